@@ -1,0 +1,304 @@
+// api.cu — the C ABI declared in include/b2pt.h.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "ctx.cuh"
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+namespace b2pt {
+
+bool cuda_fail(b2pt_ctx* ctx, cudaError_t e, const char* call, const char* file, int line) {
+    char buf[1024];
+    std::snprintf(buf, sizeof(buf), "CUDA call (%s) failed with error: '%s' (%s:%d)", call, cudaGetErrorString(e), file, line);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return false;
+}
+
+int scratch_reserve(b2pt_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) { cudaFree(ctx->scratch[slot]); ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        B2PT_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], want));
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return B2PT_OK;
+}
+
+}  // namespace b2pt
+
+using namespace b2pt;
+
+namespace {
+
+void begin_call(b2pt_ctx* ctx) {
+    double build = ctx->stats.build_seconds;
+    ctx->stats = b2pt_stats{};
+    ctx->stats.build_seconds = build;
+    cudaMemsetAsync(ctx->d_counters, 0, sizeof(TraceCounters), ctx->stream);
+    cudaEventRecord(ctx->ev0, ctx->stream);
+}
+
+int end_call(b2pt_ctx* ctx) {
+    TraceCounters c{};
+    B2PT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    B2PT_CUDA(ctx, cudaMemcpyAsync(&c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    B2PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.0f;
+    B2PT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.gpu_seconds = ms * 1e-3;
+    ctx->stats.fallback_rays += (int64_t)c.fallback;
+    ctx->stats.node_fetches += (int64_t)c.node_fetches;
+    ctx->stats.tri_fetches += (int64_t)c.tri_fetches;
+    return B2PT_OK;
+}
+
+int require_scene(b2pt_ctx* ctx, const char* who) {
+    if (!ctx) return B2PT_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = std::string(who) + ": no scene uploaded (call b2pt_upload_scene first)";
+        return B2PT_ERR_INVALID;
+    }
+    return B2PT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2pt_version(void) { return "b2pt 0.1 (sm_100a)"; }
+
+int b2pt_create(const b2pt_config* cfg, b2pt_ctx** out) {
+    if (!out) return B2PT_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("b2pt_create: no CUDA device available (") + cudaGetErrorString(e) +
+                         "); this engine has no CPU fallback";
+        return B2PT_ERR_NO_DEVICE;
+    }
+    int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= ndev) { g_create_error = "b2pt_create: device ordinal out of range"; return B2PT_ERR_INVALID; }
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) { cuda_fail(nullptr, e, "cudaGetDeviceProperties", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
+    if (prop.major != 10) {
+        char buf[512];
+        std::snprintf(buf, sizeof(buf), "b2pt_create: device %d (%s) is sm_%d%d; this library is built for sm_100a only", dev, prop.name, prop.major, prop.minor);
+        g_create_error = buf;
+        return B2PT_ERR_NO_DEVICE;
+    }
+    b2pt_ctx* ctx = new b2pt_ctx();
+    ctx->device = dev;
+    ctx->flags = cfg ? cfg->flags : 0;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_paths = (cfg && cfg->max_paths_in_flight > 0) ? cfg->max_paths_in_flight : (int64_t)(4 << 20);
+    auto fail = [&](cudaError_t err, const char* what) {
+        cuda_fail(nullptr, err, what, __FILE__, __LINE__);
+        delete ctx;
+        return B2PT_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->ev2)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->ev3)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&ctx->d_counters, sizeof(TraceCounters))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_fallback_count, 64)) != cudaSuccess) return fail(e, "cudaMalloc");
+    *out = ctx;
+    return B2PT_OK;
+}
+
+void b2pt_destroy(b2pt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    for (int i = 0; i < 16; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_fallback_count) cudaFree(ctx->d_fallback_count);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* b2pt_last_error(const b2pt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b2pt_upload_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t* mat, int64_t ntri,
+                      const b2pt_material* mats, int32_t nmat, const b2pt_light* lights, int32_t nlight) {
+    if (!ctx) return B2PT_ERR_INVALID;
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((nmat > 0 && !mats) || (nlight > 0 && !lights)) { ctx->err = "b2pt_upload_scene: NULL materials / lights"; return B2PT_ERR_INVALID; }
+    ctx->stats = b2pt_stats{};
+    return build_scene(ctx, pos, nrm, mat, ntri, mats, nmat, lights, nlight);
+}
+
+int b2pt_trace_closest_device(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n,
+                              int32_t* d_tri, float* d_t, float* d_uv) {
+    int rc = require_scene(ctx, "b2pt_trace_closest");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_o || !d_d || !d_tri))) { ctx->err = "b2pt_trace_closest: bad arguments"; return B2PT_ERR_INVALID; }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    begin_call(ctx);
+    cudaEventRecord(ctx->ev2, ctx->stream);
+    if ((rc = launch_trace_closest(ctx, d_o, d_d, d_tmax, n, d_tri, d_t, d_uv))) return rc;
+    cudaEventRecord(ctx->ev3, ctx->stream);
+    ctx->stats.extend_rays = n;
+    if ((rc = end_call(ctx))) return rc;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+    ctx->stats.trace_seconds = ms * 1e-3;
+    return B2PT_OK;
+}
+
+int b2pt_trace_any_device(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n, uint8_t* d_occ) {
+    int rc = require_scene(ctx, "b2pt_trace_any");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_o || !d_d || !d_occ))) { ctx->err = "b2pt_trace_any: bad arguments"; return B2PT_ERR_INVALID; }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    begin_call(ctx);
+    cudaEventRecord(ctx->ev2, ctx->stream);
+    if ((rc = launch_trace_any(ctx, d_o, d_d, d_tmax, n, d_occ))) return rc;
+    cudaEventRecord(ctx->ev3, ctx->stream);
+    ctx->stats.shadow_rays = n;
+    if ((rc = end_call(ctx))) return rc;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+    ctx->stats.trace_seconds = ms * 1e-3;
+    return B2PT_OK;
+}
+
+// Host-buffer variants: staged through device scratch in chunks so 100M-ray batches do not need
+// 4 GB of extra HBM at once.
+int b2pt_trace_closest(b2pt_ctx* ctx, const float* o, const float* d, const float* tmax, int64_t n,
+                       int32_t* tri, float* t, float* uv) {
+    int rc = require_scene(ctx, "b2pt_trace_closest");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!o || !d || !tri))) { ctx->err = "b2pt_trace_closest: bad arguments"; return B2PT_ERR_INVALID; }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    begin_call(ctx);
+    const int64_t chunk = 32ll << 20;
+    double trace_s = 0.0;
+    for (int64_t off = 0; off < n; off += chunk) {
+        int64_t m = std::min(chunk, n - off);
+        void *d_o, *d_d, *d_tm = nullptr, *d_tri, *d_t, *d_uv;
+        if ((rc = scratch_reserve(ctx, 1, sizeof(float) * 3 * m, &d_o))) return rc;
+        if ((rc = scratch_reserve(ctx, 2, sizeof(float) * 3 * m, &d_d))) return rc;
+        if (tmax && (rc = scratch_reserve(ctx, 3, sizeof(float) * m, &d_tm))) return rc;
+        if ((rc = scratch_reserve(ctx, 4, sizeof(int32_t) * m, &d_tri))) return rc;
+        if ((rc = scratch_reserve(ctx, 5, sizeof(float) * m, &d_t))) return rc;
+        if ((rc = scratch_reserve(ctx, 6, sizeof(float) * 2 * m, &d_uv))) return rc;
+        B2PT_CUDA(ctx, cudaMemcpyAsync(d_o, o + 3 * off, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, ctx->stream));
+        B2PT_CUDA(ctx, cudaMemcpyAsync(d_d, d + 3 * off, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, ctx->stream));
+        if (tmax) B2PT_CUDA(ctx, cudaMemcpyAsync(d_tm, tmax + off, sizeof(float) * m, cudaMemcpyHostToDevice, ctx->stream));
+        B2PT_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+        if ((rc = launch_trace_closest(ctx, (float*)d_o, (float*)d_d, (float*)d_tm, m, (int32_t*)d_tri, (float*)d_t, (float*)d_uv))) return rc;
+        B2PT_CUDA(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+        B2PT_CUDA(ctx, cudaMemcpyAsync(tri + off, d_tri, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (t) B2PT_CUDA(ctx, cudaMemcpyAsync(t + off, d_t, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (uv) B2PT_CUDA(ctx, cudaMemcpyAsync(uv + 2 * off, d_uv, sizeof(float) * 2 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        B2PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+        trace_s += ms * 1e-3;
+    }
+    ctx->stats.extend_rays = n;
+    if ((rc = end_call(ctx))) return rc;
+    ctx->stats.trace_seconds = trace_s;
+    return B2PT_OK;
+}
+
+int b2pt_trace_any(b2pt_ctx* ctx, const float* o, const float* d, const float* tmax, int64_t n, uint8_t* occluded) {
+    int rc = require_scene(ctx, "b2pt_trace_any");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!o || !d || !occluded))) { ctx->err = "b2pt_trace_any: bad arguments"; return B2PT_ERR_INVALID; }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    begin_call(ctx);
+    const int64_t chunk = 32ll << 20;
+    double trace_s = 0.0;
+    for (int64_t off = 0; off < n; off += chunk) {
+        int64_t m = std::min(chunk, n - off);
+        void *d_o, *d_d, *d_tm = nullptr, *d_occ;
+        if ((rc = scratch_reserve(ctx, 1, sizeof(float) * 3 * m, &d_o))) return rc;
+        if ((rc = scratch_reserve(ctx, 2, sizeof(float) * 3 * m, &d_d))) return rc;
+        if (tmax && (rc = scratch_reserve(ctx, 3, sizeof(float) * m, &d_tm))) return rc;
+        if ((rc = scratch_reserve(ctx, 4, m, &d_occ))) return rc;
+        B2PT_CUDA(ctx, cudaMemcpyAsync(d_o, o + 3 * off, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, ctx->stream));
+        B2PT_CUDA(ctx, cudaMemcpyAsync(d_d, d + 3 * off, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, ctx->stream));
+        if (tmax) B2PT_CUDA(ctx, cudaMemcpyAsync(d_tm, tmax + off, sizeof(float) * m, cudaMemcpyHostToDevice, ctx->stream));
+        B2PT_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+        if ((rc = launch_trace_any(ctx, (float*)d_o, (float*)d_d, (float*)d_tm, m, (uint8_t*)d_occ))) return rc;
+        B2PT_CUDA(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+        B2PT_CUDA(ctx, cudaMemcpyAsync(occluded + off, d_occ, m, cudaMemcpyDeviceToHost, ctx->stream));
+        B2PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+        trace_s += ms * 1e-3;
+    }
+    ctx->stats.shadow_rays = n;
+    if ((rc = end_call(ctx))) return rc;
+    ctx->stats.trace_seconds = trace_s;
+    return B2PT_OK;
+}
+
+int b2pt_render_device(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* settings, uint64_t seed,
+                       const b2pt_partition* part, float* d_rgb) {
+    int rc = require_scene(ctx, "b2pt_render");
+    if (rc) return rc;
+    if (!cam || !settings || !d_rgb) { ctx->err = "b2pt_render: NULL argument"; return B2PT_ERR_INVALID; }
+    if (settings->width < 2 || settings->height < 2 || settings->samples_per_pixel < 1 || settings->max_bounces < 0) {
+        ctx->err = "b2pt_render: width/height must be >= 2, samples >= 1, bounces >= 0";
+        return B2PT_ERR_INVALID;
+    }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    begin_call(ctx);
+    if ((rc = render_frame(ctx, cam, settings, seed, part, d_rgb))) return rc;
+    return end_call(ctx);
+}
+
+int b2pt_render(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* settings, uint64_t seed,
+                const b2pt_partition* part, float* rgb) {
+    if (!ctx) return B2PT_ERR_INVALID;
+    if (!settings || !rgb) { ctx->err = "b2pt_render: NULL argument"; return B2PT_ERR_INVALID; }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = sizeof(float) * 3ull * (size_t)std::max(settings->width, 0) * (size_t)std::max(settings->height, 0);
+    void* d_rgb = nullptr;
+    int rc = scratch_reserve(ctx, 7, bytes, &d_rgb);
+    if (rc) return rc;
+    if ((rc = b2pt_render_device(ctx, cam, settings, seed, part, (float*)d_rgb))) return rc;
+    B2PT_CUDA(ctx, cudaMemcpyAsync(rgb, d_rgb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B2PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2PT_OK;
+}
+
+int b2pt_tonemap(b2pt_ctx* ctx, const float* d_rgb, int64_t n_pixels, float gamma, uint8_t* rgb8) {
+    if (!ctx) return B2PT_ERR_INVALID;
+    if (!d_rgb || !rgb8 || n_pixels < 0) { ctx->err = "b2pt_tonemap: bad arguments"; return B2PT_ERR_INVALID; }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    return tonemap_frame(ctx, d_rgb, n_pixels, gamma, rgb8);
+}
+
+int b2pt_get_stats(const b2pt_ctx* ctx, b2pt_stats* out) {
+    if (!ctx || !out) return B2PT_ERR_INVALID;
+    *out = ctx->stats;
+    return B2PT_OK;
+}
+
+int b2pt_get_accel_info(const b2pt_ctx* ctx, int64_t* out5) {
+    if (!ctx || !out5) return B2PT_ERR_INVALID;
+    std::memcpy(out5, ctx->accel_info, sizeof(ctx->accel_info));
+    return B2PT_OK;
+}
+
+void* b2pt_stream(const b2pt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// ctx.cuh — device-side scene layout and the host context shared by the translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b2pt.h"
+#include "exact.cuh"
+
+namespace b2pt {
+
+// ---- HBM layout -----------------------------------------------------------------------------------
+// Triangles (reference post-build order, index == reference triangle id):
+//   tri[3*i+0] = (v0.xyz, as_float(leaf id))   tri[3*i+1] = (e1.xyz, 0)   tri[3*i+2] = (e2.xyz, 0)
+//   nrm[3*i+0] = (n0.xyz, as_float(material))  nrm[3*i+1] = (n1.xyz, 0)   nrm[3*i+2] = (n2.xyz, 0)
+// 48 B each, 16-byte vector loads.
+//
+// Reference tree (include/bvh.hpp:44-72), implicit in the order: node = range [start,end),
+// mid = start + count/2, leaf iff count <= 8.  Stored in DFS pre-order (left child = i+1):
+//   node_lo[i], node_hi[i] = exact fp32 bounds (float4, w unused)
+//   node_info[i] = (start, end, right child index or -1 for leaves, leaf id or -1)
+//   leaf_lo/leaf_hi[l]    = the same boxes, indexed by leaf id (what visibility is defined on)
+//
+// Wide BVH (8-ary collapse of the reference tree; full-precision child boxes, SoA inside the node):
+struct __align__(32) WideNode {
+    float lox[8], loy[8], loz[8];
+    float hix[8], hiy[8], hiz[8];
+    uint32_t child[8];   // 0xFFFFFFFF empty | leaf: bit31, count-1 in [30:28], first tri in [27:0] | inner: node index
+};
+static_assert(sizeof(WideNode) == 224, "WideNode layout");
+
+#define B2PT_CHILD_EMPTY 0xFFFFFFFFu
+#define B2PT_CHILD_LEAF 0x80000000u
+
+struct DMaterial { int type; float r, g, b, roughness, metallic, ior, pad; };
+struct DLight { float px, py, pz, cr, cg, cb, intensity, pad; };
+
+#define B2PT_MAX_LIGHTS 16
+
+struct DeviceScene {
+    int ntri;
+    int nnodes;
+    int nleaves;
+    int nwide;
+    const float4* tri;
+    const float4* nrm;
+    const float4* node_lo;
+    const float4* node_hi;
+    const int4* node_info;
+    const float4* leaf_lo;
+    const float4* leaf_hi;
+    const WideNode* wide;
+    const DMaterial* mats;
+    int nmat;
+    int nlight;
+    DLight lights[B2PT_MAX_LIGHTS];
+};
+
+struct HitRec { float t; int tri; float u, v; };
+
+// Per-call traversal counters (device): [0] fallback rays, [1] node fetches, [2] tri fetches.
+struct TraceCounters { unsigned long long fallback, node_fetches, tri_fetches, pad; };
+
+}  // namespace b2pt
+
+// ---- host context -----------------------------------------------------------------------------------
+struct b2pt_ctx {
+    int device = 0;
+    int flags = 0;
+    int sm_count = 0;
+    int64_t max_paths = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::string err;
+    bool has_scene = false;
+    b2pt::DeviceScene scene{};
+    // owned device allocations of the scene
+    std::vector<void*> scene_allocs;
+    // scratch (grown on demand)
+    void* scratch[16] = {};
+    size_t scratch_bytes[16] = {};
+    b2pt::TraceCounters* d_counters = nullptr;
+    int* d_fallback_count = nullptr;
+    b2pt_stats stats{};
+    int64_t accel_info[5] = {};
+};
+
+namespace b2pt {
+
+// Error plumbing: CUDA failures become "<call> failed: <cuda error> (<file>:<line>)", the text the
+// reference's CUDA_CHECK would throw (include/gpu/cuda_utils.hpp:16-25).
+bool cuda_fail(b2pt_ctx* ctx, cudaError_t e, const char* call, const char* file, int line);
+#define B2PT_CUDA(ctx, call)                                                             \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) { b2pt::cuda_fail((ctx), e__, #call, __FILE__, __LINE__); return B2PT_ERR_CUDA; } \
+    } while (0)
+
+// Scratch buffer `slot`, at least `bytes` large (contents undefined).
+int scratch_reserve(b2pt_ctx* ctx, int slot, size_t bytes, void** out);
+
+// build.cu
+int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t* mat, int64_t ntri,
+                const b2pt_material* mats, int32_t nmat, const b2pt_light* lights, int32_t nlight);
+void free_scene(b2pt_ctx* ctx);
+
+// trace.cu — all pointers device; launches on ctx->stream; counters accumulate into ctx->d_counters.
+int launch_trace_closest(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n,
+                         int32_t* d_tri, float* d_t, float* d_uv);
+int launch_trace_any(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n,
+                     uint8_t* d_occ);
+
+// render.cu
+int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st, uint64_t seed,
+                 const b2pt_partition* part, float* d_rgb);
+int tonemap_frame(b2pt_ctx* ctx, const float* d_rgb, int64_t npix, float gamma, uint8_t* rgb8_host);
+
+}  // namespace b2pt

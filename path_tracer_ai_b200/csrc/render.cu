@@ -1,0 +1,588 @@
+// render.cu — wavefront path tracer: replaces Renderer::render / tracePath /
+// calculateDirectLighting (reference include/renderer.hpp:40-102, :129-250, :252-301) and the
+// OptiX raygen / closest-hit programs (src/gpu/ptx/optix_kernels.cu:49-257).
+//
+// One frame = pixel chunks x sample chunks of at most `max_paths` camera paths.  Per chunk:
+//   k_raygen                         camera rays (camera.hpp:18-29), T = 1, L = 0
+//   for depth in 0 .. maxBounces-1:
+//     k_extend (+ k_extend_fallback)  closest hit -> hit point, shading normal, material; bins the
+//                                     path into its material queue (1-pass counting sort on the
+//                                     material type) and into the direct-light queue
+//     k_direct                        one lane per (vertex, light): shadow ray, any-hit traversal,
+//                                     light contribution; lanes of a vertex are summed in light order
+//     k_shade<DIFFUSE|SPECULAR|DIELECTRIC>  L += T*direct, BSDF sample, T update, next ray -> next queue
+//   k_resolve                        per pixel: samples added in sample order (renderer.hpp:69-72)
+// k_finalize divides by spp (renderer.hpp:75-81).
+//
+// Path state lives in SoA float4 arrays indexed by path slot p = s_local * npix_chunk + pixel_local
+// (sample-major: neighbouring threads are neighbouring pixels); queues hold path slots.  All
+// arithmetic that decides a path (hit, direction, throughput) uses the exact.cuh operations, and the
+// RNG is Philox4x32-10 keyed by (seed; pixel, sample, depth, draw): the image is a pure function of
+// (scene, camera, settings, seed), independent of chunking, queue order and GPU count.
+#include <algorithm>
+#include <cmath>
+
+#include "traverse.cuh"
+
+namespace b2pt {
+
+namespace {
+
+enum { C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_FALLBACK = 6, C_NCOUNTERS = 8 };
+
+struct Wave {
+    float4 *ro, *rd;       // ray origin / direction (direction already normalised by the Ray ctor rule)
+    float4 *g0, *g1;       // (P, material id) / (shading normal, 0)
+    float4 *direct;        // direct light at the current vertex
+    float4 *thr, *rad;     // throughput T, radiance L
+    int *q_active[2];      // active paths, ping-pong by depth parity
+    int *q_mat[3];         // per-material queues
+    int *q_shadow;         // vertices that need direct light (diffuse + specular)
+    int *q_fallback;       // closest-hit queries the fast traversal could not certify
+    int *counters;         // C_* above
+    unsigned long long* totals;   // [0] extend rays, [1] shadow rays, [2] fallback rays
+};
+
+struct CamConst {
+    V3 pos, llc, horizontal, vertical;
+};
+
+struct FrameConst {
+    int width, height;
+    int spp_total;
+    int max_bounces;
+    uint32_t k0, k1;
+    int tile_rank, tile_world, tile_area;
+};
+
+__device__ __forceinline__ long long pixel_of(const FrameConst& F, long long j) {
+    if (F.tile_world > 1) return ((j / F.tile_area) * F.tile_world + F.tile_rank) * (long long)F.tile_area + (j % F.tile_area);
+    return j;
+}
+
+// Warp-aggregated queue append; must be reached by all 32 lanes of the warp.
+__device__ __forceinline__ void warp_append(int* counter, int* queue, bool pred, int value) {
+    unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__device__ __forceinline__ V3 f4v(float4 a) { return mk3(a.x, a.y, a.z); }
+
+// renderer.hpp:308-319: rejection-sample the cube, NORMALISE the accepted point.
+__device__ __forceinline__ V3 random_in_unit_sphere(uint32_t pix, uint32_t smp, uint32_t depth, uint32_t k0, uint32_t k1) {
+    for (uint32_t k = 0;; ++k) {
+        uint4 r = philox4x32_10(pix, smp, depth, DRAW_SPHERE0 + k, k0, k1);
+        V3 p = vsub(vsmul(2.0f, mk3(u01(r.x), u01(r.y), u01(r.z))), mk3(1.0f, 1.0f, 1.0f));
+        if (vdot(p, p) < 1.0f) return vnormalize(p);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_raygen(Wave W, CamConst C, FrameConst F, long long pix_begin, int npc, int s_begin, int P) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    int s_local = p / npc, jl = p - s_local * npc;
+    long long i = pixel_of(F, pix_begin + jl);
+    int x = (int)(i % F.width), y = (int)(i / F.width);
+    uint32_t smp = (uint32_t)(s_begin + s_local);
+    uint4 j = philox4x32_10((uint32_t)i, smp, 0u, DRAW_JITTER, F.k0, F.k1);
+    float u = B2PT_DIV(B2PT_ADD((float)x, u01(j.x)), (float)(F.width - 1));     // renderer.hpp:63
+    float v = B2PT_DIV(B2PT_ADD((float)y, u01(j.y)), (float)(F.height - 1));    // renderer.hpp:64
+    // camera.hpp:28: normalize(llc + u*horizontal + v*vertical - position), then the Ray ctor again
+    V3 dir = vnormalize(vsub(vadd(vadd(C.llc, vsmul(u, C.horizontal)), vsmul(v, C.vertical)), C.pos));
+    dir = vnormalize(dir);
+    W.ro[p] = make_float4(C.pos.x, C.pos.y, C.pos.z, 0.0f);
+    W.rd[p] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+    W.thr[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    W.rad[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// After a closest hit: hit point, shading normal (normalised three times: triangle.hpp:62,
+// intersection.hpp:18, renderer.hpp:139), material lookup (renderer.hpp:141-148), binning.
+struct Epilogue { bool m0, m1, m2, shadow; };
+
+__device__ __forceinline__ Epilogue hit_epilogue(const DeviceScene& S, const Wave& W, int p, V3 o, V3 d, const HitRec& h) {
+    Epilogue e{false, false, false, false};
+    if (h.tri < 0) return e;   // miss: black background, path ends (renderer.hpp:135-137)
+    float4 a = __ldg(&S.nrm[3ll * h.tri + 0]), b = __ldg(&S.nrm[3ll * h.tri + 1]), c = __ldg(&S.nrm[3ll * h.tri + 2]);
+    float w = B2PT_SUB(B2PT_SUB(1.0f, h.u), h.v);
+    V3 n = vadd(vadd(vsmul(w, f4v(a)), vsmul(h.u, f4v(b))), vsmul(h.v, f4v(c)));
+    n = vnormalize(vnormalize(vnormalize(n)));
+    V3 P = vadd(o, vmuls(d, h.t));   // ray.hpp:14-16
+    int mat = __float_as_int(a.w);
+    if (mat < 0 || mat >= S.nmat) {
+        // invalid material id: magenta, no further bounce
+        float4 T = W.thr[p], L = W.rad[p];
+        V3 add = vmul(f4v(T), mk3(1.0f, 0.0f, 1.0f));
+        W.rad[p] = make_float4(B2PT_ADD(L.x, add.x), B2PT_ADD(L.y, add.y), B2PT_ADD(L.z, add.z), 0.0f);
+        return e;
+    }
+    int type = S.mats[mat].type;
+    W.g0[p] = make_float4(P.x, P.y, P.z, __int_as_float(mat));
+    W.g1[p] = make_float4(n.x, n.y, n.z, 0.0f);
+    e.m0 = type == B2PT_DIFFUSE; e.m1 = type == B2PT_SPECULAR; e.m2 = type == B2PT_DIELECTRIC;
+    e.shadow = e.m0 || e.m1;
+    return e;
+}
+
+__device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p) {
+    warp_append(&W.counters[C_MAT0], W.q_mat[0], e.m0, p);
+    warp_append(&W.counters[C_MAT1], W.q_mat[1], e.m1, p);
+    warp_append(&W.counters[C_MAT2], W.q_mat[2], e.m2, p);
+    warp_append(&W.counters[C_SHADOW], W.q_shadow, e.shadow, p);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
+                                                int P, TraceCounters* __restrict__ tc) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = list ? *count_ptr : P;
+    bool live = k < total;
+    Epilogue e{false, false, false, false};
+    bool fb = false;
+    int p = 0;
+    unsigned n_nodes = 0, n_tris = 0;
+    if (live) {
+        p = list ? list[k] : k;
+        float4 o4 = W.ro[p], d4 = W.rd[p];
+        RayQ r;
+        r.o = f4v(o4); r.d = f4v(d4);
+        r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
+        r.T0 = B2PT_INF;
+        HitRec h;
+        if (closest_fast<COUNT>(S, r, h, n_nodes, n_tris)) e = hit_epilogue(S, W, p, r.o, r.d, h);
+        else fb = true;
+    }
+    warp_append(&W.counters[C_FALLBACK], W.q_fallback, fb, p);
+    bin_path(W, e, p);
+    if (COUNT) {
+        for (int off = 16; off > 0; off >>= 1) {
+            n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+            n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) {
+    int total = W.counters[C_FALLBACK];
+    int rounds = (total + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (int it = 0; it < rounds; ++it) {
+        int k = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        Epilogue e{false, false, false, false};
+        int p = 0;
+        if (k < total) {
+            p = W.q_fallback[k];
+            float4 o4 = W.ro[p], d4 = W.rd[p];
+            RayQ r;
+            r.o = f4v(o4); r.d = f4v(d4);
+            r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
+            r.T0 = B2PT_INF;
+            HitRec h;
+            closest_exact_dfs(S, r, h);
+            e = hit_epilogue(S, W, p, r.o, r.d, h);
+        }
+        bin_path(W, e, p);
+    }
+}
+
+// material.hpp:28-42
+__device__ __forceinline__ float ggx_distribution(float NdotH, float roughness) {
+    if (roughness < 0.0f) roughness = 0.0f;
+    if (roughness > 1.0f) roughness = 1.0f;
+    float alpha = B2PT_MUL(roughness, roughness);
+    float alpha2 = B2PT_MUL(alpha, alpha);
+    float NdotH2 = B2PT_MUL(NdotH, NdotH);
+    float denom = B2PT_ADD(B2PT_MUL(NdotH2, B2PT_SUB(alpha2, 1.0f)), 1.0f);
+    if (denom <= 0.0f) return 0.0f;
+    return B2PT_DIV(alpha2, B2PT_MUL(B2PT_MUL(3.14159265358979323846264338327950288f, denom), denom));
+}
+// material.hpp:21-26
+__device__ __forceinline__ float schlick_fresnel(float cosTheta, float F0) {
+    float x = B2PT_SUB(1.0f, cosTheta);
+    float x2 = B2PT_MUL(x, x);
+    float x5 = B2PT_MUL(B2PT_MUL(x2, x2), x);
+    return B2PT_ADD(F0, B2PT_MUL(B2PT_SUB(1.0f, F0), x5));
+}
+
+// calculateDirectLighting (renderer.hpp:252-301).  G lanes per vertex, lane l handles light l.
+template <int G, bool COUNT>
+__global__ void __launch_bounds__(128) k_direct(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = tid / G, l = tid % G;
+    int total = W.counters[C_SHADOW];
+    bool live = k < total && l < S.nlight;
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    int addf = 0;
+    int p = 0;
+    unsigned n_nodes = 0, n_tris = 0;
+    if (k < total) p = W.q_shadow[k];
+    if (live) {
+        float4 g0 = W.g0[p], g1 = W.g1[p], d4 = W.rd[p];
+        V3 P = f4v(g0), n = f4v(g1);
+        const DMaterial m = S.mats[__float_as_int(g0.w)];
+        const DLight& lt = S.lights[l];
+        V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
+        float dist = vlength(lightDir);
+        if (!(dist < 0.0001f)) {                                          // :263-269
+            lightDir = vnormalize(lightDir);
+            RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));   // :274-275
+            if (!any_fast<COUNT>(S, r, n_nodes, n_tris)) {
+                float cosTheta = gmax(vdot(n, lightDir), 0.0f);
+                float att = B2PT_DIV(lt.intensity, B2PT_MUL(dist, dist));
+                V3 brdf;
+                if (m.type == B2PT_DIFFUSE) {
+                    brdf = vdivs(mk3(m.r, m.g, m.b), 3.14159265358979323846264338327950288f);
+                } else {
+                    V3 viewDir = vneg(f4v(d4));
+                    V3 halfVec = vnormalize(vadd(lightDir, viewDir));
+                    float NdotH = gmax(vdot(n, halfVec), 0.0f);
+                    brdf = vmuls(mk3(m.r, m.g, m.b), ggx_distribution(NdotH, m.roughness));
+                }
+                V3 c = vmuls(vmuls(vmul(mk3(lt.cr, lt.cg, lt.cb), brdf), cosTheta), att);
+                if (valid3(c)) { cx = c.x; cy = c.y; cz = c.z; addf = 1; }
+            }
+        }
+    }
+    // sum the group's contributions in light order on its first lane
+    int lane = threadIdx.x & 31, gbase = lane - l;
+    float tx = 0.0f, ty = 0.0f, tz = 0.0f;
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+        float ax = __shfl_sync(0xffffffffu, cx, gbase + q);
+        float ay = __shfl_sync(0xffffffffu, cy, gbase + q);
+        float az = __shfl_sync(0xffffffffu, cz, gbase + q);
+        int af = __shfl_sync(0xffffffffu, addf, gbase + q);
+        if (af) { tx = B2PT_ADD(tx, ax); ty = B2PT_ADD(ty, ay); tz = B2PT_ADD(tz, az); }
+    }
+    if (l == 0 && k < total) W.direct[p] = make_float4(tx, ty, tz, 0.0f);
+    if (COUNT) {
+        for (int off = 16; off > 0; off >>= 1) {
+            n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+            n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
+        }
+        if (lane == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
+    }
+}
+
+// tracePath's material switch (renderer.hpp:166-247), one kernel per material type.
+template <int TYPE>
+__global__ void __launch_bounds__(256) k_shade(DeviceScene S, Wave W, FrameConst F, long long pix_begin, int npc, int s_begin,
+                                               int depth, int next_slot) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = W.counters[C_MAT0 + TYPE];
+    bool cont = false;
+    int p = 0;
+    if (k < total) {
+        p = W.q_mat[TYPE][k];
+        float4 g0 = W.g0[p], g1 = W.g1[p], d4 = W.rd[p];
+        V3 P = f4v(g0), n = f4v(g1), d = f4v(d4);
+        const DMaterial m = S.mats[__float_as_int(g0.w)];
+        int s_local = p / npc, jl = p - s_local * npc;
+        uint32_t pix = (uint32_t)pixel_of(F, pix_begin + jl);
+        uint32_t smp = (uint32_t)(s_begin + s_local);
+        const bool last = depth + 1 >= F.max_bounces;
+        if (TYPE == B2PT_DIELECTRIC) {
+            // renderer.hpp:214-246 (direct light is dropped for dielectrics)
+            if (!last) {
+                float cosTheta = vdot(vneg(d), n);
+                float etai = 1.0f, etat = m.ior;
+                V3 normal = n;
+                if (cosTheta < 0.0f) { cosTheta = -cosTheta; float s = etai; etai = etat; etat = s; normal = vneg(normal); }
+                float sinTheta = B2PT_SQRT(B2PT_SUB(1.0f, B2PT_MUL(cosTheta, cosTheta)));
+                float ratio = B2PT_DIV(etai, etat);
+                float coin = u01(philox4x32_10(pix, smp, (uint32_t)depth, DRAW_COIN, F.k0, F.k1).x);
+                V3 dir;
+                if (B2PT_MUL(ratio, sinTheta) > 1.0f ||
+                    coin < schlick_fresnel(cosTheta, B2PT_DIV(B2PT_SUB(etai, etat), B2PT_ADD(etai, etat)))) {
+                    dir = vreflect(d, normal);
+                } else {
+                    dir = vrefract(d, normal, ratio);
+                }
+                float len = vlength(dir);
+                if (!(isnan(len) || isinf(len))) {
+                    V3 no = vadd(P, vmuls(normal, 0.001f));
+                    V3 nd = vnormalize(dir);   // Ray ctor
+                    W.ro[p] = make_float4(no.x, no.y, no.z, 0.0f);
+                    W.rd[p] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+                    cont = true;
+                }
+            }
+        } else {
+            float4 dl = W.direct[p];
+            V3 direct = f4v(dl);
+            if (valid3(direct)) {                                          // :161-163
+                V3 dir;
+                if (TYPE == B2PT_DIFFUSE) {
+                    dir = random_in_unit_sphere(pix, smp, (uint32_t)depth, F.k0, F.k1);
+                    if (vdot(dir, n) < 0.0f) dir = vneg(dir);              // :303-306
+                } else {
+                    dir = vreflect(d, n);                                  // :191
+                    if (m.roughness > 0.0f)
+                        dir = vnormalize(vadd(dir, vsmul(m.roughness, random_in_unit_sphere(pix, smp, (uint32_t)depth, F.k0, F.k1))));
+                }
+                float cosTheta = vdot(dir, n);
+                if (!(isnan(cosTheta) || isinf(cosTheta))) {
+                    float4 T4 = W.thr[p], L4 = W.rad[p];
+                    V3 T = f4v(T4), L = f4v(L4);
+                    L = vadd(L, vmul(T, direct));
+                    W.rad[p] = make_float4(L.x, L.y, L.z, 0.0f);
+                    if (!last) {
+                        V3 alb = mk3(m.r, m.g, m.b);
+                        V3 wgt;
+                        if (TYPE == B2PT_DIFFUSE) {
+                            V3 brdf = vdivs(alb, 3.14159265358979323846264338327950288f);
+                            wgt = vmuls(vmuls(vmuls(brdf, cosTheta), 2.0f), 3.14159265358979323846264338327950288f);
+                        } else {
+                            wgt = vmuls(alb, cosTheta);
+                        }
+                        T = vmul(T, wgt);
+                        V3 no = vadd(P, vmuls(n, 0.001f));
+                        V3 nd = vnormalize(dir);   // Ray ctor
+                        W.thr[p] = make_float4(T.x, T.y, T.z, 0.0f);
+                        W.ro[p] = make_float4(no.x, no.y, no.z, 0.0f);
+                        W.rd[p] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+                        cont = true;
+                    }
+                }
+            }
+        }
+    }
+    warp_append(&W.counters[next_slot], W.q_active[next_slot], cont, p);
+}
+
+// Bookkeeping between bounces (single thread): totals, reset the per-bounce counters.
+__global__ void k_begin_bounce(Wave W, int cur_slot, int first, int P, int nlight) {
+    // called BEFORE extend of a depth: the active count of this depth is known here
+    int active = first ? P : W.counters[cur_slot];
+    W.totals[0] += (unsigned long long)active;
+    W.counters[cur_slot ^ 1] = 0;
+    W.counters[C_MAT0] = 0; W.counters[C_MAT1] = 0; W.counters[C_MAT2] = 0;
+    W.counters[C_SHADOW] = 0; W.counters[C_FALLBACK] = 0;
+}
+__global__ void k_after_extend(Wave W, int nlight) {
+    W.totals[1] += (unsigned long long)W.counters[C_SHADOW] * (unsigned long long)nlight;
+    W.totals[2] += (unsigned long long)W.counters[C_FALLBACK];
+}
+
+// renderer.hpp:62-72: samples are added in sample order; invalid (NaN/Inf) samples are skipped.
+__global__ void __launch_bounds__(256) k_resolve(Wave W, float4* __restrict__ accum, long long pix_begin, int npc, int ns) {
+    int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jl >= npc) return;
+    float4 a = accum[pix_begin + jl];
+    for (int s = 0; s < ns; ++s) {
+        float4 L = W.rad[(long long)s * npc + jl];
+        if (valid3(f4v(L))) {
+            a.x = B2PT_ADD(a.x, L.x); a.y = B2PT_ADD(a.y, L.y); a.z = B2PT_ADD(a.z, L.z);
+            a.w = 1.0f;
+        }
+    }
+    accum[pix_begin + jl] = a;
+}
+
+// renderer.hpp:75-81
+__global__ void __launch_bounds__(256) k_finalize(const float4* __restrict__ accum, FrameConst F, long long nown, int all_samples, float* __restrict__ rgb) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nown) return;
+    long long i = pixel_of(F, j);
+    float4 a = accum[j];
+    float r, g, b;
+    if (a.w != 0.0f) {
+        float spp = (float)F.spp_total;
+        r = B2PT_DIV(a.x, spp); g = B2PT_DIV(a.y, spp); b = B2PT_DIV(a.z, spp);
+    } else if (all_samples) {
+        r = 1.0f; g = 0.0f; b = 1.0f;   // debug colour for pixels without a valid sample (:78)
+    } else {
+        r = g = b = 0.0f;
+    }
+    rgb[3 * i + 0] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
+}
+
+// Renderer::saveImage's tonemap (src/renderer.cpp:8-17): clamp, pow(1/gamma), truncate.
+__global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ rgb, long long n, float inv_gamma, uint8_t* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float c = rgb[i];
+    c = gmin(gmax(c, 0.0f), 1.0f);
+    c = powf(c, inv_gamma);
+    out[i] = (uint8_t)(c * 255.0f);
+}
+
+template <bool COUNT>
+void launch_direct(const DeviceScene& S, const Wave& W, int P, int nlight, cudaStream_t st, TraceCounters* tc) {
+    const int B = 128;
+    int G = 1;
+    while (G < nlight) G <<= 1;
+    long long threads = (long long)P * G;
+    unsigned grid = (unsigned)((threads + B - 1) / B);
+    switch (G) {
+        case 1: k_direct<1, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
+        case 2: k_direct<2, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
+        case 4: k_direct<4, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
+        case 8: k_direct<8, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
+        default: k_direct<16, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
+    }
+}
+
+}  // namespace
+
+int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st, uint64_t seed,
+                 const b2pt_partition* part, float* d_rgb) {
+    cudaStream_t stream = ctx->stream;
+    const DeviceScene& S = ctx->scene;
+    const int W_ = st->width, H_ = st->height;
+    const long long npix = (long long)W_ * H_;
+
+    FrameConst F{};
+    F.width = W_; F.height = H_; F.spp_total = st->samples_per_pixel; F.max_bounces = st->max_bounces;
+    F.k0 = (uint32_t)seed; F.k1 = (uint32_t)(seed >> 32);
+    int tile_world = part ? part->tile_world : 0, tile_rank = part ? part->tile_rank : 0;
+    int tile_size = (part && part->tile_size > 0) ? part->tile_size : 32;
+    if (tile_world > 1 && (tile_rank < 0 || tile_rank >= tile_world)) { ctx->err = "b2pt_render: tile_rank out of range"; return B2PT_ERR_INVALID; }
+    F.tile_world = tile_world > 1 ? tile_world : 1; F.tile_rank = tile_world > 1 ? tile_rank : 0; F.tile_area = tile_size * tile_size;
+    int s_begin = part ? part->sample_begin : 0;
+    int s_count = (part && part->sample_count > 0) ? part->sample_count : st->samples_per_pixel - s_begin;
+    if (s_begin < 0 || s_count < 0 || s_begin + s_count > st->samples_per_pixel) { ctx->err = "b2pt_render: sample range out of bounds"; return B2PT_ERR_INVALID; }
+    const int all_samples = (s_begin == 0 && s_count == st->samples_per_pixel) ? 1 : 0;
+
+    // owned pixels: runs of tile_area consecutive pixels (row-major), run k -> rank k % world
+    long long nown = npix;
+    if (F.tile_world > 1) {
+        long long A = F.tile_area, nruns = (npix + A - 1) / A;
+        long long mine = (nruns - F.tile_rank + F.tile_world - 1) / F.tile_world;   // runs r, r+w, ...
+        nown = mine * A;
+        long long last_run = (mine - 1) * F.tile_world + F.tile_rank;
+        if (mine > 0 && last_run == nruns - 1) nown -= nruns * A - npix;   // the frame's final, partial run
+        if (mine <= 0) nown = 0;
+    }
+
+    // camera constants, host fp32 in the order of camera.hpp:19-26
+    CamConst C{};
+    {
+        auto v = [](const float* p) { return mk3(p[0], p[1], p[2]); };
+        V3 pos = v(cam->position), fwd = v(cam->forward), right = v(cam->right), up = v(cam->up);
+        float theta = cam->fov * 0.01745329251994329576923690768489f;
+        float h = std::tan(theta / 2.0f);
+        float vh = 2.0f * h;
+        float vw = vh * (16.0f / 9.0f);
+        V3 hor = mk3(vw * right.x, vw * right.y, vw * right.z);
+        V3 ver = mk3(vh * up.x, vh * up.y, vh * up.z);
+        V3 llc = mk3(pos.x - hor.x / 2.0f - ver.x / 2.0f + fwd.x, pos.y - hor.y / 2.0f - ver.y / 2.0f + fwd.y,
+                     pos.z - hor.z / 2.0f - ver.z / 2.0f + fwd.z);
+        C.pos = pos; C.llc = llc; C.horizontal = hor; C.vertical = ver;
+    }
+
+    B2PT_CUDA(ctx, cudaMemsetAsync(d_rgb, 0, sizeof(float) * 3 * npix, stream));
+    ctx->stats.samples = nown * s_count;
+    if (nown == 0 || s_count == 0) return B2PT_OK;
+
+    // chunking
+    long long maxp = std::max<long long>(ctx->max_paths, 1024);
+    int npc_max = (int)std::min<long long>(nown, maxp);
+    int ns_max = (int)std::max<long long>(1, std::min<long long>(s_count, maxp / npc_max));
+    long long Pmax = (long long)npc_max * ns_max;
+
+    // scratch: slot 8 = path state + queues, slot 9 = accumulators, slot 10 = counters/totals
+    size_t f4 = sizeof(float4) * (size_t)Pmax, qi = sizeof(int) * (size_t)Pmax;
+    void* base = nullptr;
+    int rc = scratch_reserve(ctx, 8, 7 * f4 + 7 * qi + 1024, &base);
+    if (rc) return rc;
+    Wave Wv{};
+    {
+        char* b = (char*)base;
+        Wv.ro = (float4*)b; b += f4; Wv.rd = (float4*)b; b += f4; Wv.g0 = (float4*)b; b += f4; Wv.g1 = (float4*)b; b += f4;
+        Wv.direct = (float4*)b; b += f4; Wv.thr = (float4*)b; b += f4; Wv.rad = (float4*)b; b += f4;
+        Wv.q_active[0] = (int*)b; b += qi; Wv.q_active[1] = (int*)b; b += qi;
+        Wv.q_mat[0] = (int*)b; b += qi; Wv.q_mat[1] = (int*)b; b += qi; Wv.q_mat[2] = (int*)b; b += qi;
+        Wv.q_shadow = (int*)b; b += qi; Wv.q_fallback = (int*)b; b += qi;
+    }
+    void* accum = nullptr;
+    if ((rc = scratch_reserve(ctx, 9, sizeof(float4) * (size_t)nown, &accum))) return rc;
+    void* cnt = nullptr;
+    if ((rc = scratch_reserve(ctx, 10, 256, &cnt))) return rc;
+    Wv.counters = (int*)cnt;
+    Wv.totals = (unsigned long long*)((char*)cnt + 128);
+    B2PT_CUDA(ctx, cudaMemsetAsync(cnt, 0, 256, stream));
+    B2PT_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(float4) * (size_t)nown, stream));
+
+    const bool count = (ctx->flags & B2PT_FLAG_COUNT_FETCHES) != 0;
+    int64_t launches = 0;
+    float trace_ms = 0.0f;
+    // Traversal time is measured with events around extend+direct of every bounce; to avoid a sync
+    // per bounce the events are created once per call and read at the end.
+    std::vector<cudaEvent_t> evs;
+    auto ev = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); evs.push_back(e); };
+
+    for (long long pix_begin = 0; pix_begin < nown; pix_begin += npc_max) {
+        int npc = (int)std::min<long long>(npc_max, nown - pix_begin);
+        for (int sb = 0; sb < s_count; sb += ns_max) {
+            int ns = std::min(ns_max, s_count - sb);
+            int P = npc * ns;
+            int sabs = s_begin + sb;
+            k_raygen<<<(P + 255) / 256, 256, 0, stream>>>(Wv, C, F, pix_begin, npc, sabs, P);
+            ++launches;
+            for (int depth = 0; depth < st->max_bounces; ++depth) {
+                int cur = depth & 1;
+                k_begin_bounce<<<1, 1, 0, stream>>>(Wv, cur, depth == 0, P, S.nlight);
+                const int* list = depth == 0 ? nullptr : Wv.q_active[cur];
+                ev();
+                if (count) k_extend<true><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                else k_extend<false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                k_extend_fallback<<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
+                k_after_extend<<<1, 1, 0, stream>>>(Wv, S.nlight);
+                if (S.nlight > 0) {
+                    if (count) launch_direct<true>(S, Wv, P, S.nlight, stream, ctx->d_counters);
+                    else launch_direct<false>(S, Wv, P, S.nlight, stream, ctx->d_counters);
+                    ++launches;
+                }
+                ev();
+                int nxt = cur ^ 1;
+                k_shade<B2PT_DIFFUSE><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
+                k_shade<B2PT_SPECULAR><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
+                k_shade<B2PT_DIELECTRIC><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
+                launches += 7;
+            }
+            k_resolve<<<(npc + 255) / 256, 256, 0, stream>>>(Wv, (float4*)accum, pix_begin, npc, ns);
+            ++launches;
+        }
+    }
+    k_finalize<<<(unsigned)((nown + 255) / 256), 256, 0, stream>>>((const float4*)accum, F, nown, all_samples, d_rgb);
+    ++launches;
+    cudaError_t le = cudaGetLastError();
+    unsigned long long totals[3] = {0, 0, 0};
+    cudaError_t ce = cudaMemcpyAsync(totals, Wv.totals, sizeof(totals), cudaMemcpyDeviceToHost, stream);
+    cudaError_t se = cudaStreamSynchronize(stream);
+    for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, evs[i], evs[i + 1]) == cudaSuccess) trace_ms += ms;
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    if (le != cudaSuccess) { cuda_fail(ctx, le, "render kernels", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
+    if (ce != cudaSuccess) { cuda_fail(ctx, ce, "cudaMemcpyAsync(totals)", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
+    if (se != cudaSuccess) { cuda_fail(ctx, se, "cudaStreamSynchronize", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
+    ctx->stats.extend_rays = (int64_t)totals[0];
+    ctx->stats.shadow_rays = (int64_t)totals[1];
+    ctx->stats.fallback_rays = (int64_t)totals[2];
+    ctx->stats.kernel_launches = launches;
+    ctx->stats.trace_seconds = trace_ms * 1e-3;
+    return B2PT_OK;
+}
+
+int tonemap_frame(b2pt_ctx* ctx, const float* d_rgb, int64_t npix, float gamma, uint8_t* rgb8_host) {
+    void* d_out = nullptr;
+    int rc = scratch_reserve(ctx, 11, (size_t)npix * 3, &d_out);
+    if (rc) return rc;
+    long long n = npix * 3;
+    if (n > 0) k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_rgb, n, 1.0f / gamma, (uint8_t*)d_out);
+    B2PT_CUDA(ctx, cudaGetLastError());
+    B2PT_CUDA(ctx, cudaMemcpyAsync(rgb8_host, d_out, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    B2PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2PT_OK;
+}
+
+}  // namespace b2pt

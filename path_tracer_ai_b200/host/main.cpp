@@ -1,0 +1,143 @@
+// main.cpp — command line of the B200 path tracer: same flags, short forms and defaults as the
+// reference's src/main.cpp:13-24 (cxxopts there; a small parser here since cxxopts is absent):
+//   -m/--mode {cpu,gpu} (gpu)  -w/--width (800)  -h/--height (450; note: -h is height, not help)
+//   -s/--samples (100)  -b/--bounces (5)  -g/--gamma (2.2)  -i/--input (IronMan/IronMan.obj)
+//   -o/--output (output.png)  --help
+// Extras: --seed N (default 1234), --device N, --dump-float FILE (raw float32 W*H*3 framebuffer).
+// Same flow as src/main.cpp:39-96: Scene -> loadFromObj -> fixed Camera -> renderer -> saveImage,
+// timing uploadScene + render.  Differences, by design: --mode cpu is refused (this binary has no
+// CPU renderer; the reference CPU path lives in oracle/ as test infrastructure) and a GPU failure is
+// an error exit, not a silent CPU fallback (reference src/main.cpp:98-113 removed).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <string>
+
+#include "b200_renderer.hpp"
+#include "camera.hpp"
+#include "scene.hpp"
+
+namespace {
+
+struct Opt { const char* longName; char shortName; bool takesValue; const char* def; const char* help; };
+const Opt kOpts[] = {
+    {"mode", 'm', true, "gpu", "Rendering mode (cpu/gpu)"},
+    {"width", 'w', true, "800", "Image width"},
+    {"height", 'h', true, "450", "Image height"},
+    {"samples", 's', true, "100", "Samples per pixel"},
+    {"bounces", 'b', true, "5", "Maximum ray bounces"},
+    {"gamma", 'g', true, "2.2", "Gamma correction value"},
+    {"input", 'i', true, "IronMan/IronMan.obj", "Input OBJ file path"},
+    {"output", 'o', true, "output.png", "Output image file path"},
+    {"seed", 0, true, "1234", "RNG seed (Philox key)"},
+    {"device", 0, true, "0", "CUDA device ordinal"},
+    {"dump-float", 0, true, "", "Also write the float framebuffer (raw float32, W*H*3)"},
+    {"help", 0, false, "", "Print help"},
+};
+
+void printHelp() {
+    std::cout << "GPU path tracer for NVIDIA B200 (sm_100a)\nUsage:\n  b2pt_cli [OPTION...]\n\n";
+    for (const Opt& o : kOpts) {
+        std::string flag = o.shortName ? std::string("  -") + o.shortName + ", --" + o.longName : std::string("      --") + o.longName;
+        if (o.takesValue) flag += " arg";
+        std::printf("%-28s %s%s%s%s\n", flag.c_str(), o.help, (o.def[0] ? " (default: " : ""), o.def, (o.def[0] ? ")" : ""));
+    }
+}
+
+bool parseArgs(int argc, char** argv, std::map<std::string, std::string>& out, std::string& err) {
+    for (const Opt& o : kOpts) if (o.takesValue) out[o.longName] = o.def;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        const Opt* opt = nullptr;
+        std::string value;
+        bool haveValue = false;
+        if (a.rfind("--", 0) == 0) {
+            std::string name = a.substr(2);
+            size_t eq = name.find('=');
+            if (eq != std::string::npos) { value = name.substr(eq + 1); name = name.substr(0, eq); haveValue = true; }
+            for (const Opt& o : kOpts) if (name == o.longName) opt = &o;
+        } else if (a.size() >= 2 && a[0] == '-') {
+            for (const Opt& o : kOpts) if (o.shortName && a[1] == o.shortName) opt = &o;
+            if (a.size() > 2) { value = a.substr(a[2] == '=' ? 3 : 2); haveValue = true; }
+        }
+        if (!opt) { err = "Option '" + a + "' does not exist"; return false; }
+        if (!opt->takesValue) { out[opt->longName] = "true"; continue; }
+        if (!haveValue) {
+            if (i + 1 >= argc) { err = std::string("Option '") + opt->longName + "' is missing an argument"; return false; }
+            value = argv[++i];
+        }
+        out[opt->longName] = value;
+    }
+    return true;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    try {
+        std::map<std::string, std::string> args;
+        std::string err;
+        if (!parseArgs(argc, argv, args, err)) { std::cerr << "Error: " << err << std::endl; return -1; }
+        if (args.count("help")) { printHelp(); return 0; }
+
+        const std::string mode = args["mode"], inputFile = args["input"], outputFile = args["output"];
+        if (mode != "cpu" && mode != "gpu") {
+            std::cerr << "Invalid rendering mode. Use 'cpu' or 'gpu'." << std::endl;   // main.cpp:114-117
+            return -1;
+        }
+        if (mode == "cpu") {
+            std::cerr << "--mode cpu is not available in this build: the engine is GPU-only and has no CPU fallback. "
+                         "Use --mode gpu (the default)." << std::endl;
+            return -1;
+        }
+
+        b2pt::Scene scene;
+        std::cout << "Loading model from: " << inputFile << std::endl;
+        if (!scene.loadFromObj(inputFile)) {
+            std::cerr << "Failed to load model: " << inputFile << std::endl;   // main.cpp:40-43
+            return -1;
+        }
+        std::cout << "- Total triangles: " << scene.getTriangles().size() << "\n- Total materials: " << scene.getMaterials().size() << std::endl;
+
+        // main.cpp:46-51
+        b2pt::Camera camera(b2pt::vec3(0.0f, 2.0f, 5.0f), b2pt::vec3(0.0f, 1.8f, 0.0f), b2pt::vec3(0.0f, 1.0f, 0.0f), 45.0f);
+
+        b2pt::B200Renderer::Settings settings;
+        settings.width = std::atoi(args["width"].c_str());
+        settings.height = std::atoi(args["height"].c_str());
+        settings.samplesPerPixel = std::atoi(args["samples"].c_str());
+        settings.maxBounces = std::atoi(args["bounces"].c_str());
+        settings.gamma = static_cast<float>(std::atof(args["gamma"].c_str()));
+
+        b2pt::B200Renderer renderer(settings, std::atoi(args["device"].c_str()), std::strtoull(args["seed"].c_str(), nullptr, 10));
+        renderer.initialize();
+
+        auto t0 = std::chrono::high_resolution_clock::now();
+        renderer.uploadScene(scene);
+        renderer.render(camera);
+        auto t1 = std::chrono::high_resolution_clock::now();
+        double secs = std::chrono::duration<double>(t1 - t0).count();
+        b2pt_stats s = renderer.stats();
+        std::cout << "\nRendering completed in " << secs << " seconds" << std::endl;
+        std::printf("{\"samples\": %lld, \"extend_rays\": %lld, \"shadow_rays\": %lld, \"fallback_rays\": %lld, \"gpu_seconds\": %.6f, "
+                    "\"msamples_per_s\": %.3f, \"mrays_per_s\": %.3f}\n",
+                    (long long)s.samples, (long long)s.extend_rays, (long long)s.shadow_rays, (long long)s.fallback_rays, s.gpu_seconds,
+                    s.samples / s.gpu_seconds * 1e-6, (s.extend_rays + s.shadow_rays) / s.gpu_seconds * 1e-6);
+
+        renderer.saveImage(outputFile);
+        if (!args["dump-float"].empty()) {
+            FILE* f = std::fopen(args["dump-float"].c_str(), "wb");
+            if (!f) { std::cerr << "Error: cannot write " << args["dump-float"] << std::endl; return -1; }
+            std::fwrite(renderer.frameBuffer().data(), sizeof(float), renderer.frameBuffer().size(), f);
+            std::fclose(f);
+        }
+        std::cout << "Image saved as: " << outputFile << std::endl;
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "Error: " << e.what() << std::endl;   // no CPU fallback
+        return -1;
+    }
+}
