@@ -102,6 +102,10 @@ typedef struct b2pt_stats {
     double gpu_seconds;       /* CUDA-event time of the call's device work */
     double trace_seconds;     /* CUDA-event time spent in extend + shadow traversal kernels */
     double build_seconds;     /* (upload) acceleration-structure build, device time */
+    double extend_seconds;    /* part of trace_seconds spent in closest-hit kernels (incl. exact fallback) */
+    double shadow_seconds;    /* part of trace_seconds spent in the direct-light / any-hit kernels */
+    int64_t extend_launches;  /* closest-hit kernel launches (fast kernel only) */
+    int64_t shadow_launches;  /* direct-light / any-hit kernel launches */
 } b2pt_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------- */

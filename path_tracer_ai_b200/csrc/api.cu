@@ -156,7 +156,8 @@ int b2pt_trace_closest_device(b2pt_ctx* ctx, const float* d_o, const float* d_d,
     if ((rc = end_call(ctx))) return rc;
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
-    ctx->stats.trace_seconds = ms * 1e-3;
+    ctx->stats.trace_seconds = ctx->stats.extend_seconds = ms * 1e-3;
+    ctx->stats.extend_launches = (n + (1ll << 30) - 1) >> 30;
     return B2PT_OK;
 }
 
@@ -173,7 +174,8 @@ int b2pt_trace_any_device(b2pt_ctx* ctx, const float* d_o, const float* d_d, con
     if ((rc = end_call(ctx))) return rc;
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
-    ctx->stats.trace_seconds = ms * 1e-3;
+    ctx->stats.trace_seconds = ctx->stats.shadow_seconds = ms * 1e-3;
+    ctx->stats.shadow_launches = (n + (1ll << 30) - 1) >> 30;
     return B2PT_OK;
 }
 
@@ -213,7 +215,8 @@ int b2pt_trace_closest(b2pt_ctx* ctx, const float* o, const float* d, const floa
     }
     ctx->stats.extend_rays = n;
     if ((rc = end_call(ctx))) return rc;
-    ctx->stats.trace_seconds = trace_s;
+    ctx->stats.trace_seconds = ctx->stats.extend_seconds = trace_s;
+    ctx->stats.extend_launches = (n + chunk - 1) / chunk;
     return B2PT_OK;
 }
 
@@ -246,7 +249,8 @@ int b2pt_trace_any(b2pt_ctx* ctx, const float* o, const float* d, const float* t
     }
     ctx->stats.shadow_rays = n;
     if ((rc = end_call(ctx))) return rc;
-    ctx->stats.trace_seconds = trace_s;
+    ctx->stats.trace_seconds = ctx->stats.shadow_seconds = trace_s;
+    ctx->stats.shadow_launches = (n + chunk - 1) / chunk;
     return B2PT_OK;
 }
 

@@ -511,8 +511,8 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     B2PT_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(float4) * (size_t)nown, stream));
 
     const bool count = (ctx->flags & B2PT_FLAG_COUNT_FETCHES) != 0;
-    int64_t launches = 0;
-    float trace_ms = 0.0f;
+    int64_t launches = 0, n_extend = 0, n_shadow = 0;
+    float extend_ms = 0.0f, shadow_ms = 0.0f;
     // Traversal time is measured with events around extend+direct of every bounce; to avoid a sync
     // per bounce the events are created once per call and read at the end.
     std::vector<cudaEvent_t> evs;
@@ -535,7 +535,10 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 else k_extend<false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 k_extend_fallback<<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
                 k_after_extend<<<1, 1, 0, stream>>>(Wv, S.nlight);
+                ev();
+                ++n_extend;
                 if (S.nlight > 0) {
+                    ++n_shadow;
                     if (count) launch_direct<true>(S, Wv, P, S.nlight, stream, ctx->d_counters);
                     else launch_direct<false>(S, Wv, P, S.nlight, stream, ctx->d_counters);
                     ++launches;
@@ -557,9 +560,10 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     unsigned long long totals[3] = {0, 0, 0};
     cudaError_t ce = cudaMemcpyAsync(totals, Wv.totals, sizeof(totals), cudaMemcpyDeviceToHost, stream);
     cudaError_t se = cudaStreamSynchronize(stream);
-    for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+    for (size_t i = 0; i + 2 < evs.size(); i += 3) {   // per bounce: before extend, after extend, after direct
         float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, evs[i], evs[i + 1]) == cudaSuccess) trace_ms += ms;
+        if (cudaEventElapsedTime(&ms, evs[i], evs[i + 1]) == cudaSuccess) extend_ms += ms;
+        if (cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]) == cudaSuccess) shadow_ms += ms;
     }
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
     if (le != cudaSuccess) { cuda_fail(ctx, le, "render kernels", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
@@ -569,7 +573,11 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     ctx->stats.shadow_rays = (int64_t)totals[1];
     ctx->stats.fallback_rays = (int64_t)totals[2];
     ctx->stats.kernel_launches = launches;
-    ctx->stats.trace_seconds = trace_ms * 1e-3;
+    ctx->stats.extend_seconds = extend_ms * 1e-3;
+    ctx->stats.shadow_seconds = shadow_ms * 1e-3;
+    ctx->stats.trace_seconds = (extend_ms + shadow_ms) * 1e-3;
+    ctx->stats.extend_launches = n_extend;
+    ctx->stats.shadow_launches = n_shadow;
     return B2PT_OK;
 }
 

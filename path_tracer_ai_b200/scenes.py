@@ -1,7 +1,10 @@
 """Procedural scenes for the BASELINE.json configurations (synthetic data, seeded).
 
 * :func:`write_cornell_obj`  — configs 1/2: a ~42-triangle Cornell-style box (diffuse walls, rough-specular tall
-  box, glass short box, diffuse wedge) written as OBJ+MTL for ``Scene::loadFromObj``.
+  box, glass short box, diffuse wedge) written as OBJ+MTL for ``Scene::loadFromObj``.  The tall box defaults to
+  roughness 0.4: the reference's direct term for SPECULAR is albedo * D_GGX with no normalisation
+  (renderer.hpp:286-290), whose peak 1/(pi*rough^4) is ~3000 at roughness 0.1 — an estimator so heavy-tailed that
+  the reference does not agree with ITSELF to 30 % at 1024 spp; 0.4 keeps statistical parity tests meaningful.
 * :func:`mesh_scene`         — configs 3/5: displaced terrain + tessellated, noise-displaced tori / spheres with
   mixed materials, generated directly as triangle arrays in world space.
 * :func:`random_rays`        — config 4: origins uniform in the inflated scene box, directions uniform on the sphere.
@@ -77,7 +80,7 @@ def _wedge(cx, cz, s, h, y0, angle_deg):
     return np.array(v, np.float64), f
 
 
-def cornell_geometry(seed: int = 1234):
+def cornell_geometry(seed: int = 1234, steel: str = "rough0.4_steel"):
     """Returns (vertices[n,3] in post-flip model coords, faces[(i,j,k)], face material names, materials dict)."""
     rng = np.random.default_rng(seed)
     verts, faces, fmat = [], [], []
@@ -99,7 +102,7 @@ def cornell_geometry(seed: int = 1234):
     add(shell, [(0, 4, 7), (0, 7, 3)], "diffuse_red")        # left wall, normal +x
     add(shell, [(1, 2, 6), (1, 6, 5)], "diffuse_green")      # right wall, normal -x
     v, f = _box(-0.35, -0.15, 0.28, 1.15, 0.22, -Y + 1e-3, 17.0)
-    add(v, f, "rough0.1_steel")
+    add(v, f, steel)
     v, f = _box(0.38, 0.12, 0.26, 0.55, 0.24, -Y + 1e-3, -19.0)
     add(v, f, "glass_box")
     v, f = _wedge(-0.05, 0.36, 0.16, 0.3, -Y + 1e-3, 33.0)
@@ -117,17 +120,17 @@ def cornell_geometry(seed: int = 1234):
         "diffuse_red": dict(Kd=(0.65, 0.05, 0.05)),
         "diffuse_green": dict(Kd=(0.12, 0.45, 0.15)),
         "diffuse_blue": dict(Kd=(0.15, 0.25, 0.7)),
-        "rough0.1_steel": dict(Kd=(0.8, 0.8, 0.85)),
+        steel: dict(Kd=(0.8, 0.8, 0.85)),
         "glass_box": dict(Kd=(1.0, 1.0, 1.0), Ni=1.5),
     }
     return V, faces, fmat, materials
 
 
-def write_cornell_obj(directory: str, seed: int = 1234, name: str = "cornell") -> str:
+def write_cornell_obj(directory: str, seed: int = 1234, name: str = "cornell", steel: str = "rough0.4_steel") -> str:
     """Writes <name>.obj/.mtl.  File z is the NEGATED model z because Scene::loadFromObj flips z
     (reference src/scene.cpp:237): after loading, the box opens toward the camera and face normals
     (computed by the loader from the transformed vertices, :251-256) point outward."""
-    V, faces, fmat, materials = cornell_geometry(seed)
+    V, faces, fmat, materials = cornell_geometry(seed, steel)
     os.makedirs(directory, exist_ok=True)
     obj_path = os.path.join(directory, name + ".obj")
     with open(os.path.join(directory, name + ".mtl"), "w") as f:

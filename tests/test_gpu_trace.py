@@ -1,0 +1,217 @@
+"""GPU parity tests for the query path (replaces Scene::intersect): every call goes through the C ABI
+(b2pt_trace_closest / b2pt_trace_any) and is compared BIT-EXACTLY with the CPU oracle — triangle ids,
+hit/miss, the fp32 bits of t and of the barycentrics."""
+import os
+
+import numpy as np
+import pytest
+
+import path_tracer_ai_b200 as pt
+from oracle import PortOracle
+from path_tracer_ai_b200 import scenes
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rays(n, seed, extent=1.2, centre=(0, 0, 0)):
+    rng = np.random.default_rng(seed)
+    o = (rng.random((n, 3)) * 2 * extent - extent + np.asarray(centre)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    return o, d
+
+
+def check_closest(eng, P, o, d, tmax=None):
+    tri, t, uv = eng.trace_closest(o, d, tmax)
+    rt, rtt, ruv = P.trace_closest(o, d, tmax)
+    assert np.array_equal(tri, rt), f"{int((tri != rt).sum())} of {len(tri)} ids differ"
+    assert np.array_equal(bits(t), bits(rtt))
+    assert np.array_equal(bits(uv), bits(ruv))
+    return tri
+
+
+def upload(eng, P):
+    pos, nrm, mat = P.triangles()
+    eng.upload_scene(pos, nrm, mat)
+
+
+@pytest.mark.parametrize("ntri", [0, 1, 7, 8, 9, 16, 17, 65, 1000])
+def test_small_and_ragged_triangle_counts(engine, ntri):
+    pos = scenes.random_soup(ntri, 10 + ntri, size=0.8)
+    P = PortOracle(pos)
+    assert np.array_equal(pt.reference_order(pos), P.order())
+    upload(engine, P)
+    o, d = rays(30011, ntri)   # ragged: not a multiple of the block size
+    check_closest(engine, P, o, d)
+    occ = engine.trace_any(o, d)
+    assert np.array_equal(occ, P.trace_any(o, d))
+
+
+def test_zero_rays(engine):
+    P = PortOracle(scenes.random_soup(100, 1))
+    upload(engine, P)
+    tri, t, uv = engine.trace_closest(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert tri.shape == (0,) and t.shape == (0,)
+
+
+def test_soup_closest_and_any(engine):
+    pos = scenes.random_soup(50000, 3)
+    P = PortOracle(pos)
+    upload(engine, P)
+    o, d = rays(500000, 4)
+    tri = check_closest(engine, P, o, d)
+    assert (tri >= 0).mean() > 0.3
+    st = engine.stats()
+    assert st["extend_rays"] == len(o) and st["kernel_launches"] >= 1
+    tmax = np.random.default_rng(9).random(len(o)).astype(np.float32) * 1.5
+    check_closest(engine, P, o, d, tmax)
+    assert np.array_equal(engine.trace_any(o, d, tmax), P.trace_any(o, d, tmax))
+
+
+def test_mesh_scene_with_vertex_aimed_rays(engine):
+    """Tessellated mesh with shared vertices; half of the rays are aimed exactly at mesh vertices so that
+    edge/vertex hits, bit-equal ties and leaf-box-face hits (the cases the fast kernel must hand to the exact
+    kernel) actually occur."""
+    ms = scenes.mesh_scene(120000, seed=2)
+    P = PortOracle(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
+    pos, nrm, mat = P.triangles()
+    engine.upload_scene(pos, nrm, mat, ms["materials8"])
+    o, d = scenes.random_rays(400000, ms["lo"], ms["hi"], 5)
+    V = ms["pos"].reshape(-1, 3)
+    rng = np.random.default_rng(6)
+    half = len(o) // 2
+    d[:half] = V[rng.integers(0, len(V), half)] - o[:half]
+    check_closest(engine, P, o, d)
+
+
+def test_axis_aligned_geometry_reference_quirks(engine):
+    """An axis-aligned plane (all its reference leaves are flat => invisible to the reference, aabb.hpp:21) plus
+    an axis-aligned box sitting in a soup: the engine must reproduce the reference's answer, quirks included."""
+    g = 24
+    xs, zs = np.meshgrid(np.arange(g, dtype=np.float32), np.arange(g, dtype=np.float32), indexing="ij")
+    a = np.stack([xs, np.zeros_like(xs), zs], -1).reshape(-1, 3)
+    plane = np.concatenate([np.concatenate([a, a + [1, 0, 0], a + [1, 0, 1]], 1),
+                            np.concatenate([a, a + [1, 0, 1], a + [0, 0, 1]], 1)]).astype(np.float32) * np.float32(0.1) - np.float32(1.2)
+    V, f = scenes._box(0.0, 0.0, 0.4, 0.8, 0.4, -0.4, 0.0)
+    box = np.array([np.concatenate([V[i], V[j], V[k]]) for (i, j, k) in f], np.float32)
+    pos = np.concatenate([plane, box, scenes.random_soup(3000, 5)])
+    P = PortOracle(pos)
+    upload(engine, P)
+    o, d = rays(400000, 12, extent=1.5)
+    check_closest(engine, P, o, d)
+    # rays straight down / along axes (zero direction components -> inf / NaN slabs)
+    o2 = o.copy()
+    d2 = np.zeros_like(d)
+    d2[:, 1] = -1.0
+    d2[::3] = [1.0, 0.0, 0.0]
+    d2[1::3] = [0.0, 0.0, -1.0]
+    check_closest(engine, P, o2, d2)
+    assert np.array_equal(engine.trace_any(o2, d2), P.trace_any(o2, d2))
+    assert engine.stats()["shadow_rays"] == len(o2)
+
+
+def test_exact_only_kernel_agrees(built):
+    """B2PT_FLAG_EXACT_ONLY routes everything through the flattened reference recursion."""
+    eng = pt.Engine(flags=pt.FLAG_EXACT_ONLY)
+    pos = scenes.random_soup(20000, 8)
+    P = PortOracle(pos)
+    upload(eng, P)
+    o, d = rays(200000, 3)
+    check_closest(eng, P, o, d)
+    eng.close()
+
+
+def test_fetch_counters(built):
+    eng = pt.Engine(flags=pt.FLAG_COUNT_FETCHES)
+    pos = scenes.random_soup(20000, 8)
+    P = PortOracle(pos)
+    upload(eng, P)
+    o, d = rays(100000, 3)
+    check_closest(eng, P, o, d)
+    st = eng.stats()
+    assert st["node_fetches"] >= len(o) and st["tri_fetches"] > 0
+    eng.close()
+
+
+def test_golden_vectors_from_the_reference(engine):
+    """tests/golden/*.npz were produced by the reference itself (oracle/_ref)."""
+    g = np.load(os.path.join(GOLD, "trace_soup.npz"))
+    order = pt.reference_order(g["pos"])
+    assert np.array_equal(order, g["order"])
+    engine.upload_scene(g["pos"][order])
+    tri, t, _ = engine.trace_closest(g["o"], g["d"])
+    assert np.array_equal(tri, g["tri"]) and np.array_equal(bits(t), g["t_bits"])
+    tri, t, _ = engine.trace_closest(g["o"], g["d"], g["tmax"])
+    assert np.array_equal(tri, g["tri_tmax"]) and np.array_equal(bits(t), g["t_tmax_bits"])
+    g = np.load(os.path.join(GOLD, "trace_cornell.npz"))
+    order = pt.reference_order(g["pos"])
+    assert np.array_equal(order, g["order"])
+    engine.upload_scene(g["pos"][order], g["nrm"][order], g["mat"][order])
+    tri, t, _ = engine.trace_closest(g["o"], g["d"])
+    assert np.array_equal(tri, g["tri"]) and np.array_equal(bits(t), g["t_bits"])
+
+
+def test_device_pointer_entry_points(engine):
+    import torch
+    pos = scenes.random_soup(5000, 8)
+    P = PortOracle(pos)
+    upload(engine, P)
+    o, d = rays(100000, 3)
+    dev = torch.device("cuda:0")
+    to, td = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+    tri = torch.empty(len(o), dtype=torch.int32, device=dev)
+    t = torch.empty(len(o), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    engine.trace_closest_device(to.data_ptr(), td.data_ptr(), None, len(o), tri.data_ptr(), t.data_ptr(), None)
+    rt, rtt, _ = P.trace_closest(o, d)
+    assert np.array_equal(tri.cpu().numpy(), rt) and np.array_equal(bits(t.cpu().numpy()), bits(rtt))
+
+
+def test_call_order_errors(built):
+    eng = pt.Engine()
+    with pytest.raises(pt.B2ptError, match="no scene uploaded"):
+        eng.trace_closest(np.zeros((1, 3), np.float32), np.ones((1, 3), np.float32))
+    with pytest.raises(pt.B2ptError, match="no scene uploaded"):
+        eng.render(pt.Camera().c, 16, 9, 1, 1)
+    eng.close()
+
+
+def test_full_size_properties_1m_triangles(engine):
+    """BASELINE config 4 scale (1M triangles, 8M rays here): oracle-checked on a stratified 200k subset, plus
+    size-independent properties on the whole batch — determinism (64-bit hash of ids+t), t consistent with the
+    winning triangle's plane, any-hit(tmax = t*(1+eps)) true exactly where closest hits, false with tmax < t."""
+    ms = scenes.mesh_scene(1_000_000, seed=1234)
+    order = pt.reference_order(ms["pos"])
+    pos = ms["pos"][order]
+    engine.upload_scene(pos, ms["nrm"][order], ms["mat"][order], ms["materials8"])
+    n = 8_000_000
+    o, d = scenes.random_rays(n, ms["lo"], ms["hi"], 99)
+    tri, t, uv = engine.trace_closest(o, d)
+    st = engine.stats()
+    assert st["fallback_rays"] < n // 1000
+    tri2, t2, _ = engine.trace_closest(o, d)
+    assert np.array_equal(tri, tri2) and np.array_equal(bits(t), bits(t2))
+    hit = tri >= 0
+    assert 0.2 < hit.mean() < 0.95
+    # geometric consistency: o + d_n * t lies on the winning triangle (barycentric reconstruction)
+    dn = d / np.linalg.norm(d.astype(np.float64), axis=1, keepdims=True)
+    Ph = o[hit] + dn[hit] * t[hit, None]
+    T = pos[tri[hit]].reshape(-1, 3, 3).astype(np.float64)
+    u, v = uv[hit, 0:1].astype(np.float64), uv[hit, 1:2].astype(np.float64)
+    Pb = T[:, 0] * (1 - u - v) + T[:, 1] * u + T[:, 2] * v
+    assert np.abs(Ph - Pb).max() < 2e-3
+    # occlusion consistency
+    tm = np.where(hit, t * np.float32(1.001), np.float32(1.0)).astype(np.float32)
+    occ = engine.trace_any(o, d, tm)
+    assert np.array_equal(occ[hit], np.ones(int(hit.sum()), np.uint8))
+    tm2 = np.where(hit, t * np.float32(0.999), np.float32(0.002)).astype(np.float32)
+    occ2 = engine.trace_any(o[hit], d[hit], tm2[hit])
+    assert occ2.sum() == 0
+    # oracle on a stratified subset
+    P = PortOracle(ms["pos"], None, None)
+    assert np.array_equal(P.order(), order)
+    sel = np.arange(0, n, n // 200000)[:200000]
+    rt, rtt, _ = P.trace_closest(o[sel], d[sel])
+    assert np.array_equal(tri[sel], rt) and np.array_equal(bits(t[sel]), bits(rtt))

@@ -1,0 +1,150 @@
+"""CPU-only tests of the host side in front of the GPU engine: reference BVH ordering, OBJ/MTL loader and
+scene normalisation (vs the reference-harness loader), camera, PNG writer, CLI argument contract."""
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle
+import path_tracer_ai_b200 as pt
+from oracle import PortOracle, RefOracle
+from path_tracer_ai_b200 import scenes
+
+from conftest import bits
+
+needs_ref = pytest.mark.skipif(not (oracle.ref_available() or os.path.isdir("/root/reference/include")),
+                               reason="oracle/_ref not built and /root/reference absent")
+
+
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 1), (8, 2), (9, 3), (1000, 4), (65537, 5)])
+def test_reference_order_matches_oracle(built, n, seed):
+    pos = scenes.random_soup(n, seed)
+    assert np.array_equal(pt.reference_order(pos), PortOracle(pos).order())
+
+
+@needs_ref
+def test_reference_order_matches_reference(built):
+    ms = scenes.mesh_scene(20000, seed=9)
+    assert np.array_equal(pt.reference_order(ms["pos"]), RefOracle(ms["pos"]).order())
+
+
+@needs_ref
+def test_loader_matches_reference_loader(built, tmp_path):
+    obj = scenes.write_cornell_obj(str(tmp_path))
+    sc = pt.Scene()
+    assert sc.loadFromObj(obj)
+    R = RefOracle(obj_path=obj)
+    rp, rn, rm = R.triangles()
+    assert len(sc.pos) == 50 and R.tree_stats()["flat"] == 0
+    assert np.array_equal(bits(rp), bits(sc.pos)) and np.array_equal(bits(rn), bits(sc.nrm)) and np.array_equal(rm, sc.mat)
+    assert np.array_equal(bits(R.materials()), bits(sc.materials8))
+    assert sc.lights == [tuple(map(tuple, l[:2])) + (l[2],) for l in pt.REFERENCE_LIGHTS] or len(sc.lights) == 4
+
+
+def test_loader_obj_features(built, tmp_path):
+    """Quads / polygons (fan triangulation), negative indices, v/vt/vn forms, missing MTL, reference name rules."""
+    (tmp_path / "m.mtl").write_text(
+        "newmtl shiny_red_paint\nKd 0.1 0.2 0.3\n\nnewmtl gold_trim\nKd 0.5 0.5 0.5\n\nnewmtl plain\nKd 0.25 0.5 1.0\n\n"
+        "newmtl glass_pane\nKd 1 1 1\nNi 1.33\n\nnewmtl rough0.25_x\nKd 0.4 0.4 0.4\n\nnewmtl darksilver_bolt\nKd 0 0 0\n")
+    (tmp_path / "s.obj").write_text(
+        "mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 2 0.5\nvn 0 0 1\nvt 0.5 0.5\n"
+        "usemtl shiny_red_paint\nf 1 2 3 4\n"            # quad -> 2 triangles
+        "usemtl gold_trim\nf -5//1 -4//1 -3//1\n"        # negative indices, v//vn
+        "usemtl plain\nf 1/1/1 2/1/1 5/1/1\n"
+        "usemtl glass_pane\nf 1 3 5\nusemtl rough0.25_x\nf 2 3 5\nusemtl darksilver_bolt\nf 1 2 3 4 5\n"   # pentagon -> 3
+        "usemtl nosuch\nf 1 2 3\n")
+    sc = pt.Scene()
+    assert sc.loadFromObj(str(tmp_path / "s.obj"))
+    assert len(sc.pos) == 8 + 2 + 1 + 1 + 1 + 1 + 3 + 1
+    m = sc.materials8
+    assert m.shape[0] == 2 + 6
+    assert m[0, 0] == 1 and np.allclose(m[0, 1:4], [0.9, 0.2, 0.2])          # default red specular (scene.cpp:58-63)
+    assert m[1, 0] == 0 and np.allclose(m[1, 1:4], 0.9)                        # wall (scene.cpp:66-71)
+    assert m[2, 0] == 1 and np.allclose(m[2, 1:4], [0.9, 0.2, 0.2]) and np.isclose(m[2, 4], 0.1)    # contains "red"
+    assert np.allclose(m[3, 1:4], [1.0, 0.8, 0.0]) and np.isclose(m[3, 4], 0.05)                   # "gold"
+    want = np.clip(np.power(np.float32([0.25, 0.5, 1.0]), np.float32(0.8)) * np.float32(1.2), 0, 1)
+    assert m[4, 0] == 1 and np.allclose(m[4, 1:4], want, atol=1e-6)            # pow(Kd, .8) * 1.2 clamped
+    assert m[5, 0] == 2 and np.isclose(m[5, 6], 1.33)                          # extension: glass*
+    assert m[6, 0] == 1 and np.isclose(m[6, 4], 0.25)                          # extension: rough<value>*
+    assert np.allclose(m[7, 1:4], 0.95)                                        # "silver" (darksilver)
+    pre_mat = np.empty_like(sc.mat)
+    pre_mat[sc.order] = sc.mat
+    assert list(pre_mat[:8]) == [1] * 8                                        # the room comes first
+    assert list(pre_mat[8:]) == [2, 2, 3, 4, 5, 6, 7, 7, 7, 2]                 # unknown usemtl -> -1 -> 0 -> +2
+    assert not pt.Scene().loadFromObj(str(tmp_path / "missing.obj"))
+    # normalisation: model scaled to 3 units, centred, z flipped, lifted 1.8 (scene.cpp:47-52, :236-238)
+    pre_pos = np.empty_like(sc.pos)
+    pre_pos[sc.order] = sc.pos
+    model = pre_pos[8:].reshape(-1, 3)
+    assert np.isclose(model[:, 1].max() - model[:, 1].min(), 3.0, atol=1e-5)
+    assert np.isclose((model[:, 1].max() + model[:, 1].min()) / 2, 1.8, atol=1e-5)
+
+
+def test_camera_matches_oracle(built):
+    cam = pt.Camera()
+    want = PortOracle.camera()
+    got = np.concatenate([cam.getPosition(), cam.getForward(), cam.getRight(), cam.getUp(), [cam.getFOV()]]).astype(np.float32)
+    assert np.array_equal(bits(got), bits(want))
+    cam2 = pt.Camera((1, 2, 3), (0.5, -1, 0.25), (0.1, 1, 0), 60.0)
+    want2 = PortOracle.camera((1, 2, 3), (0.5, -1, 0.25), (0.1, 1, 0), 60.0)
+    got2 = np.concatenate([cam2.getPosition(), cam2.getForward(), cam2.getRight(), cam2.getUp(), [60.0]]).astype(np.float32)
+    assert np.array_equal(bits(got2), bits(want2))
+
+
+def test_png_writer_roundtrip(built, tmp_path):
+    from path_tracer_ai_b200.renderer import _host_lib
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (13, 37, 3), dtype=np.uint8)
+    p = tmp_path / "x.png"
+    assert _host_lib().b2pt_write_png(os.fsencode(str(p)), 37, 13, img.ctypes.data) == 0
+    data = p.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, ihdr = 8, b"", None
+    while pos < len(data):
+        (ln,) = struct.unpack(">I", data[pos:pos + 4])
+        typ, body = data[pos + 4:pos + 8], data[pos + 8:pos + 8 + ln]
+        (crc,) = struct.unpack(">I", data[pos + 8 + ln:pos + 12 + ln])
+        assert zlib.crc32(typ + body) == crc
+        if typ == b"IHDR":
+            ihdr = struct.unpack(">IIBBBBB", body)
+        if typ == b"IDAT":
+            idat += body
+        pos += 12 + ln
+    assert ihdr == (37, 13, 8, 2, 0, 0, 0)
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(13, 1 + 37 * 3)
+    assert (raw[:, 0] == 0).all() and np.array_equal(raw[:, 1:].reshape(13, 37, 3), img)
+
+
+def cli():
+    return os.path.join(os.path.dirname(pt.LIB_PATH), "b2pt_cli")
+
+
+def test_cli_contract(built, tmp_path):
+    """Flag names / defaults / exit codes of the reference's src/main.cpp:13-43, :114-117."""
+    r = subprocess.run([cli(), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0
+    for flag in ("-m, --mode", "-w, --width", "-h, --height", "-s, --samples", "-b, --bounces", "-g, --gamma", "-i, --input",
+                 "-o, --output", "--help"):
+        assert flag in r.stdout
+    for default in ("gpu", "800", "450", "100", "5", "2.2", "IronMan/IronMan.obj", "output.png"):
+        assert f"(default: {default})" in r.stdout
+    r = subprocess.run([cli(), "--mode", "vulkan"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Invalid rendering mode" in r.stderr
+    r = subprocess.run([cli(), "-m", "cpu"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    r = subprocess.run([cli(), "-i", str(tmp_path / "nope.obj")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Failed to load model" in r.stderr
+    r = subprocess.run([cli(), "--frobnicate"], capture_output=True, text=True)
+    assert r.returncode != 0
+
+
+def test_cli_without_gpu_fails_loudly(built, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    obj = scenes.write_cornell_obj(str(tmp_path))
+    r = subprocess.run([cli(), "-i", obj, "-w", "16", "--height=9", "-s2"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
