@@ -86,7 +86,8 @@ def test_render_independent_of_chunking_and_partition(built, cornell):
 
 def test_invalid_material_id_is_magenta(engine):
     """renderer.hpp:141-148: a hit whose material id is out of range returns (1, 0, 1)."""
-    pos = np.array([[-5, -5, 0, 5, -5, 0, 0, 5, 0]], np.float32) + np.float32([0, 1.8, 0] * 3)
+    # tilted: an axis-aligned (flat-box) triangle would be invisible to the reference (aabb.hpp:21)
+    pos = np.array([[-5, -5, -0.5, 5, -5, -0.5, 0, 5, 0.5]], np.float32) + np.float32([0, 1.8, 0] * 3)
     nrm = np.tile(np.float32([0, 0, 1]), 3)[None]
     engine.upload_scene(pos, nrm, np.array([7], np.int32), np.zeros((1, 8), np.float32))
     fb = engine.render(pt.Camera().c, 16, 9, 2, 3, seed=1)
