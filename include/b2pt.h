@@ -89,6 +89,7 @@ typedef struct b2pt_config {
 
 #define B2PT_FLAG_COUNT_FETCHES 1  /* instrumented traversal: count node / triangle fetches (slower) */
 #define B2PT_FLAG_EXACT_ONLY 2     /* closest-hit queries use only the exact reference-order DFS kernel */
+#define B2PT_FLAG_OCTET 4          /* batch queries use the 8-lanes-per-ray cooperative kernels instead of one ray per lane */
 
 /* Counters of the last trace / render call. */
 typedef struct b2pt_stats {

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libb2pt.so")
 DIFFUSE, SPECULAR, DIELECTRIC = 0, 1, 2
 FLAG_COUNT_FETCHES = 1
 FLAG_EXACT_ONLY = 2
+FLAG_OCTET = 4
 
 
 class Material(C.Structure):

@@ -5,11 +5,12 @@
 // One frame = pixel chunks x sample chunks of at most `max_paths` camera paths.  Per chunk:
 //   k_raygen                         camera rays (camera.hpp:18-29), T = 1, L = 0
 //   for depth in 0 .. maxBounces-1:
-//     k_extend (+ k_extend_fallback)  closest hit -> hit point, shading normal, material; bins the
-//                                     path into its material queue (1-pass counting sort on the
-//                                     material type) and into the direct-light queue
-//     k_direct                        one lane per (vertex, light): shadow ray, any-hit traversal,
-//                                     light contribution; lanes of a vertex are summed in light order
+//     k_extend (+ k_extend_fallback)  closest hit, warp-cooperative (8 lanes per ray, persistent octets)
+//     k_hitinfo                       hit point, shading normal, material; bins the path into its material
+//                                     queue (1-pass counting sort on the material type) and into the
+//                                     direct-light queue
+//     k_direct                        one octet per (vertex, light): shadow ray, cooperative any-hit
+//                                     traversal, light contribution; a vertex's lights are summed in order
 //     k_shade<DIFFUSE|SPECULAR|DIELECTRIC>  L += T*direct, BSDF sample, T update, next ray -> next queue
 //   k_resolve                        per pixel: samples added in sample order (renderer.hpp:69-72)
 // k_finalize divides by spp (renderer.hpp:75-81).
@@ -28,10 +29,11 @@ namespace b2pt {
 
 namespace {
 
-enum { C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_FALLBACK = 6, C_NCOUNTERS = 8 };
+enum { C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_FALLBACK = 6, C_NEXT = 7, C_NCOUNTERS = 8 };
 
 struct Wave {
     float4 *ro, *rd;       // ray origin / direction (direction already normalised by the Ray ctor rule)
+    float4 *hit;           // closest hit of the current bounce: (t, tri id, u, v)
     float4 *g0, *g1;       // (P, material id) / (shading normal, 0)
     float4 *direct;        // direct light at the current vertex
     float4 *thr, *rad;     // throughput T, radiance L
@@ -137,30 +139,42 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
     warp_append(&W.counters[C_SHADOW], W.q_shadow, e.shadow, p);
 }
 
+#define B2PT_WF_BLOCK 128
+#define B2PT_WF_OCTETS (B2PT_WF_BLOCK / 8)
+#define B2PT_WF_BATCH 8
+
+// Closest hit for the active paths: persistent octets (8 lanes per ray) claim B2PT_WF_BATCH queue entries
+// per atomic.  Writes the hit record; uncertified rays go to the fallback queue.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
-                                                int P, TraceCounters* __restrict__ tc) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = list ? *count_ptr : P;
-    bool live = k < total;
-    Epilogue e{false, false, false, false};
-    bool fb = false;
-    int p = 0;
+__global__ void __launch_bounds__(B2PT_WF_BLOCK) k_extend(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
+                                                          int P, TraceCounters* __restrict__ tc) {
+    __shared__ uint2 stacks[B2PT_WF_OCTETS * B2PT_STACK_PITCH];
+    OctetCtx g = make_octet(stacks);
+    const int total = list ? *count_ptr : P;
     unsigned n_nodes = 0, n_tris = 0;
-    if (live) {
-        p = list ? list[k] : k;
-        float4 o4 = W.ro[p], d4 = W.rd[p];
-        RayQ r;
-        r.o = f4v(o4); r.d = f4v(d4);
-        r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
-        r.T0 = B2PT_INF;
-        HitRec h;
-        if (closest_fast<COUNT>(S, r, h, n_nodes, n_tris)) e = hit_epilogue(S, W, p, r.o, r.d, h);
-        else fb = true;
+    while (true) {
+        int base = 0;
+        if (g.gl == 0) base = atomicAdd(&W.counters[C_NEXT], B2PT_WF_BATCH);
+        base = __shfl_sync(g.gmask, base, g.gbase);
+        if (base >= total) break;
+        int end = min(base + B2PT_WF_BATCH, total);
+        for (int k = base; k < end; ++k) {
+            int p = list ? list[k] : k;
+            float4 o4 = W.ro[p], d4 = W.rd[p];
+            RayQ r;
+            r.o = f4v(o4); r.d = f4v(d4);
+            r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
+            r.T0 = B2PT_INF;
+            HitRec h;
+            bool ok = closest_octet<COUNT>(S, g, r, h, n_nodes, n_tris);
+            if (g.gl == 0) {
+                W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+                if (!ok) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
+            }
+        }
     }
-    warp_append(&W.counters[C_FALLBACK], W.q_fallback, fb, p);
-    bin_path(W, e, p);
     if (COUNT) {
+        __syncwarp();
         for (int off = 16; off > 0; off >>= 1) {
             n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
             n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
@@ -169,26 +183,36 @@ __global__ void __launch_bounds__(128) k_extend(DeviceScene S, Wave W, const int
     }
 }
 
+// The rays the cooperative kernel could not certify: the flattened reference recursion, one thread per ray.
 __global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) {
     int total = W.counters[C_FALLBACK];
-    int rounds = (total + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
-    for (int it = 0; it < rounds; ++it) {
-        int k = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-        Epilogue e{false, false, false, false};
-        int p = 0;
-        if (k < total) {
-            p = W.q_fallback[k];
-            float4 o4 = W.ro[p], d4 = W.rd[p];
-            RayQ r;
-            r.o = f4v(o4); r.d = f4v(d4);
-            r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
-            r.T0 = B2PT_INF;
-            HitRec h;
-            closest_exact_dfs(S, r, h);
-            e = hit_epilogue(S, W, p, r.o, r.d, h);
-        }
-        bin_path(W, e, p);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        int p = W.q_fallback[k];
+        float4 o4 = W.ro[p], d4 = W.rd[p];
+        RayQ r;
+        r.o = f4v(o4); r.d = f4v(d4);
+        r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
+        r.T0 = B2PT_INF;
+        HitRec h;
+        closest_exact_dfs(S, r, h);
+        W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
     }
+}
+
+// Hit record -> hit point / shading normal / material, and the one-pass counting sort by material type.
+__global__ void __launch_bounds__(256) k_hitinfo(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr, int P) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = list ? *count_ptr : P;
+    Epilogue e{false, false, false, false};
+    int p = 0;
+    if (k < total) {
+        p = list ? list[k] : k;
+        float4 h4 = W.hit[p], o4 = W.ro[p], d4 = W.rd[p];
+        HitRec h;
+        h.t = h4.x; h.tri = __float_as_int(h4.y); h.u = h4.z; h.v = h4.w;
+        e = hit_epilogue(S, W, p, f4v(o4), f4v(d4), h);
+    }
+    bin_path(W, e, p);
 }
 
 // material.hpp:28-42
@@ -210,58 +234,76 @@ __device__ __forceinline__ float schlick_fresnel(float cosTheta, float F0) {
     return B2PT_ADD(F0, B2PT_MUL(B2PT_SUB(1.0f, F0), x5));
 }
 
-// calculateDirectLighting (renderer.hpp:252-301).  G lanes per vertex, lane l handles light l.
-template <int G, bool COUNT>
-__global__ void __launch_bounds__(128) k_direct(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = tid / G, l = tid % G;
-    int total = W.counters[C_SHADOW];
-    bool live = k < total && l < S.nlight;
-    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
-    int addf = 0;
-    int p = 0;
+// calculateDirectLighting (renderer.hpp:252-301).  One octet (8 lanes) per (vertex, light): the octet builds
+// the shadow ray, runs the cooperative any-hit traversal and evaluates the light's contribution; GPV octets
+// of a warp share a vertex and their contributions are summed in light order (more than GPV lights: rounds).
+template <int GPV, bool COUNT>
+__global__ void __launch_bounds__(B2PT_WF_BLOCK) k_direct(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
+    __shared__ uint2 stacks[B2PT_WF_OCTETS * B2PT_STACK_PITCH];
+    OctetCtx g = make_octet(stacks);
+    const int total = W.counters[C_SHADOW];
+    const int lane = threadIdx.x & 31, octet = lane >> 3;
+    const int vslot = octet / GPV, lsub = octet % GPV;
+    constexpr int VPW = 4 / GPV;   // vertices per warp and iteration
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned n_nodes = 0, n_tris = 0;
-    if (k < total) p = W.q_shadow[k];
-    if (live) {
-        float4 g0 = W.g0[p], g1 = W.g1[p], d4 = W.rd[p];
-        V3 P = f4v(g0), n = f4v(g1);
-        const DMaterial m = S.mats[__float_as_int(g0.w)];
-        const DLight& lt = S.lights[l];
-        V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
-        float dist = vlength(lightDir);
-        if (!(dist < 0.0001f)) {                                          // :263-269
-            lightDir = vnormalize(lightDir);
-            RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));   // :274-275
-            if (!any_fast<COUNT>(S, r, n_nodes, n_tris)) {
-                float cosTheta = gmax(vdot(n, lightDir), 0.0f);
-                float att = B2PT_DIV(lt.intensity, B2PT_MUL(dist, dist));
-                V3 brdf;
-                if (m.type == B2PT_DIFFUSE) {
-                    brdf = vdivs(mk3(m.r, m.g, m.b), 3.14159265358979323846264338327950288f);
-                } else {
-                    V3 viewDir = vneg(f4v(d4));
-                    V3 halfVec = vnormalize(vadd(lightDir, viewDir));
-                    float NdotH = gmax(vdot(n, halfVec), 0.0f);
-                    brdf = vmuls(mk3(m.r, m.g, m.b), ggx_distribution(NdotH, m.roughness));
+    for (int vbase = warp * VPW; vbase < total; vbase += nwarps * VPW) {
+        const int k = vbase + vslot;
+        const bool live = k < total;
+        int p = 0;
+        V3 P = mk3(0, 0, 0), n = mk3(0, 0, 0), viewDir = mk3(0, 0, 0);
+        DMaterial m{};
+        if (live) {
+            p = W.q_shadow[k];
+            float4 g0 = W.g0[p], g1 = W.g1[p], d4 = W.rd[p];
+            P = f4v(g0); n = f4v(g1); viewDir = vneg(f4v(d4));
+            m = S.mats[__float_as_int(g0.w)];
+        }
+        float tx = 0.0f, ty = 0.0f, tz = 0.0f;
+        for (int l0 = 0; l0 < S.nlight; l0 += GPV) {
+            const int l = l0 + lsub;
+            float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+            int addf = 0;
+            if (live && l < S.nlight) {
+                const DLight& lt = S.lights[l];
+                V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
+                float dist = vlength(lightDir);
+                if (!(dist < 0.0001f)) {                                          // :263-269
+                    lightDir = vnormalize(lightDir);
+                    RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));   // :274-275
+                    int occ = any_octet<COUNT>(S, g, r, n_nodes, n_tris);
+                    if (occ < 0) { HitRec h; closest_exact_dfs(S, r, h); occ = h.tri >= 0; }
+                    if (!occ) {
+                        float cosTheta = gmax(vdot(n, lightDir), 0.0f);
+                        float att = B2PT_DIV(lt.intensity, B2PT_MUL(dist, dist));
+                        V3 brdf;
+                        if (m.type == B2PT_DIFFUSE) {
+                            brdf = vdivs(mk3(m.r, m.g, m.b), 3.14159265358979323846264338327950288f);
+                        } else {
+                            V3 halfVec = vnormalize(vadd(lightDir, viewDir));
+                            float NdotH = gmax(vdot(n, halfVec), 0.0f);
+                            brdf = vmuls(mk3(m.r, m.g, m.b), ggx_distribution(NdotH, m.roughness));
+                        }
+                        V3 c = vmuls(vmuls(vmul(mk3(lt.cr, lt.cg, lt.cb), brdf), cosTheta), att);
+                        if (valid3(c)) { cx = c.x; cy = c.y; cz = c.z; addf = 1; }
+                    }
                 }
-                V3 c = vmuls(vmuls(vmul(mk3(lt.cr, lt.cg, lt.cb), brdf), cosTheta), att);
-                if (valid3(c)) { cx = c.x; cy = c.y; cz = c.z; addf = 1; }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < GPV; ++q) {
+                int src = (vslot * GPV + q) * 8;
+                float ax = __shfl_sync(0xffffffffu, cx, src);
+                float ay = __shfl_sync(0xffffffffu, cy, src);
+                float az = __shfl_sync(0xffffffffu, cz, src);
+                int af = __shfl_sync(0xffffffffu, addf, src);
+                if (af) { tx = B2PT_ADD(tx, ax); ty = B2PT_ADD(ty, ay); tz = B2PT_ADD(tz, az); }
             }
         }
+        if (live && lsub == 0 && g.gl == 0) W.direct[p] = make_float4(tx, ty, tz, 0.0f);
     }
-    // sum the group's contributions in light order on its first lane
-    int lane = threadIdx.x & 31, gbase = lane - l;
-    float tx = 0.0f, ty = 0.0f, tz = 0.0f;
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-        float ax = __shfl_sync(0xffffffffu, cx, gbase + q);
-        float ay = __shfl_sync(0xffffffffu, cy, gbase + q);
-        float az = __shfl_sync(0xffffffffu, cz, gbase + q);
-        int af = __shfl_sync(0xffffffffu, addf, gbase + q);
-        if (af) { tx = B2PT_ADD(tx, ax); ty = B2PT_ADD(ty, ay); tz = B2PT_ADD(tz, az); }
-    }
-    if (l == 0 && k < total) W.direct[p] = make_float4(tx, ty, tz, 0.0f);
     if (COUNT) {
+        __syncwarp();
         for (int off = 16; off > 0; off >>= 1) {
             n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
             n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
@@ -363,7 +405,7 @@ __global__ void k_begin_bounce(Wave W, int cur_slot, int first, int P, int nligh
     W.totals[0] += (unsigned long long)active;
     W.counters[cur_slot ^ 1] = 0;
     W.counters[C_MAT0] = 0; W.counters[C_MAT1] = 0; W.counters[C_MAT2] = 0;
-    W.counters[C_SHADOW] = 0; W.counters[C_FALLBACK] = 0;
+    W.counters[C_SHADOW] = 0; W.counters[C_FALLBACK] = 0; W.counters[C_NEXT] = 0;
 }
 __global__ void k_after_extend(Wave W, int nlight) {
     W.totals[1] += (unsigned long long)W.counters[C_SHADOW] * (unsigned long long)nlight;
@@ -414,18 +456,15 @@ __global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ rgb, 
 }
 
 template <bool COUNT>
-void launch_direct(const DeviceScene& S, const Wave& W, int P, int nlight, cudaStream_t st, TraceCounters* tc) {
-    const int B = 128;
-    int G = 1;
-    while (G < nlight) G <<= 1;
-    long long threads = (long long)P * G;
-    unsigned grid = (unsigned)((threads + B - 1) / B);
-    switch (G) {
-        case 1: k_direct<1, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
-        case 2: k_direct<2, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
-        case 4: k_direct<4, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
-        case 8: k_direct<8, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
-        default: k_direct<16, COUNT><<<grid, B, 0, st>>>(S, W, tc); break;
+void launch_direct(const DeviceScene& S, const Wave& W, int P, int nlight, int sm_count, cudaStream_t st, TraceCounters* tc) {
+    int gpv = nlight >= 4 ? 4 : (nlight >= 2 ? 2 : 1);
+    long long warps = ((long long)P * gpv + 3) / 4;
+    unsigned grid = (unsigned)std::min<long long>((warps + 3) / 4, (long long)sm_count * 16);
+    if (grid == 0) grid = 1;
+    switch (gpv) {
+        case 1: k_direct<1, COUNT><<<grid, B2PT_WF_BLOCK, 0, st>>>(S, W, tc); break;
+        case 2: k_direct<2, COUNT><<<grid, B2PT_WF_BLOCK, 0, st>>>(S, W, tc); break;
+        default: k_direct<4, COUNT><<<grid, B2PT_WF_BLOCK, 0, st>>>(S, W, tc); break;
     }
 }
 
@@ -490,12 +529,12 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     // scratch: slot 8 = path state + queues, slot 9 = accumulators, slot 10 = counters/totals
     size_t f4 = sizeof(float4) * (size_t)Pmax, qi = sizeof(int) * (size_t)Pmax;
     void* base = nullptr;
-    int rc = scratch_reserve(ctx, 8, 7 * f4 + 7 * qi + 1024, &base);
+    int rc = scratch_reserve(ctx, 8, 8 * f4 + 7 * qi + 1024, &base);
     if (rc) return rc;
     Wave Wv{};
     {
         char* b = (char*)base;
-        Wv.ro = (float4*)b; b += f4; Wv.rd = (float4*)b; b += f4; Wv.g0 = (float4*)b; b += f4; Wv.g1 = (float4*)b; b += f4;
+        Wv.ro = (float4*)b; b += f4; Wv.rd = (float4*)b; b += f4; Wv.hit = (float4*)b; b += f4; Wv.g0 = (float4*)b; b += f4; Wv.g1 = (float4*)b; b += f4;
         Wv.direct = (float4*)b; b += f4; Wv.thr = (float4*)b; b += f4; Wv.rad = (float4*)b; b += f4;
         Wv.q_active[0] = (int*)b; b += qi; Wv.q_active[1] = (int*)b; b += qi;
         Wv.q_mat[0] = (int*)b; b += qi; Wv.q_mat[1] = (int*)b; b += qi; Wv.q_mat[2] = (int*)b; b += qi;
@@ -531,16 +570,21 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 k_begin_bounce<<<1, 1, 0, stream>>>(Wv, cur, depth == 0, P, S.nlight);
                 const int* list = depth == 0 ? nullptr : Wv.q_active[cur];
                 ev();
-                if (count) k_extend<true><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                else k_extend<false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                {
+                    long long octets = ((long long)P + B2PT_WF_BATCH - 1) / B2PT_WF_BATCH;
+                    unsigned egrid = (unsigned)std::min<long long>((octets + B2PT_WF_OCTETS - 1) / B2PT_WF_OCTETS, (long long)ctx->sm_count * 16);
+                    if (count) k_extend<true><<<egrid, B2PT_WF_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else k_extend<false><<<egrid, B2PT_WF_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                }
                 k_extend_fallback<<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
+                k_hitinfo<<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
                 k_after_extend<<<1, 1, 0, stream>>>(Wv, S.nlight);
                 ev();
                 ++n_extend;
                 if (S.nlight > 0) {
                     ++n_shadow;
-                    if (count) launch_direct<true>(S, Wv, P, S.nlight, stream, ctx->d_counters);
-                    else launch_direct<false>(S, Wv, P, S.nlight, stream, ctx->d_counters);
+                    if (count) launch_direct<true>(S, Wv, P, S.nlight, ctx->sm_count, stream, ctx->d_counters);
+                    else launch_direct<false>(S, Wv, P, S.nlight, ctx->sm_count, stream, ctx->d_counters);
                     ++launches;
                 }
                 ev();
@@ -548,7 +592,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 k_shade<B2PT_DIFFUSE><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
                 k_shade<B2PT_SPECULAR><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
                 k_shade<B2PT_DIELECTRIC><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
-                launches += 7;
+                launches += 8;
             }
             k_resolve<<<(npc + 255) / 256, 256, 0, stream>>>(Wv, (float4*)accum, pix_begin, npc, ns);
             ++launches;

@@ -1,18 +1,23 @@
 // trace.cu — batch ray queries: replaces Scene::intersect (reference include/scene.hpp:96-99) for
 // caller-supplied ray batches (BASELINE config 4: the closest-hit microbench).
 //
-// Two-phase, bit-exact: k_closest_fast traverses the 8-wide BVH and certifies its answer; rays it
-// cannot certify (bit-equal ties, winner on its own leaf box's entry face) are appended to a
+// Two-phase, bit-exact: k_closest_octet traverses the 8-wide BVH cooperatively (8 lanes per ray,
+// persistent octets that fetch rays in batches from a global counter) and certifies its answer; rays
+// it cannot certify (bit-equal ties, winner on its own leaf box's entry face) are appended to a
 // fallback list and re-run by k_closest_exact, the flattened reference recursion.
 #include <algorithm>
-#include "traverse.cuh"
+#include "traverse_thread.cuh"
 
 namespace b2pt {
 
 namespace {
 
+#define B2PT_TRACE_BLOCK 128
+#define B2PT_OCTETS_PER_BLOCK (B2PT_TRACE_BLOCK / 8)
+#define B2PT_RAY_BATCH 8        // rays an octet claims per atomic
+
 __device__ __forceinline__ void flush_counters(TraceCounters* c, unsigned n_nodes, unsigned n_tris) {
-    // warp-aggregate then one atomic per warp
+    // warp-aggregate then one atomic per warp (all lanes converged by the caller's __syncwarp)
     for (int off = 16; off > 0; off >>= 1) {
         n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
         n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
@@ -36,21 +41,34 @@ __device__ __forceinline__ void store_hit(const HitRec& h, long long i, int32_t*
     if (uv) { uv[2 * i] = h.u; uv[2 * i + 1] = h.v; }
 }
 
+// Persistent octets: each claims B2PT_RAY_BATCH consecutive rays at a time.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_closest_fast(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
-                                                      const float* __restrict__ tmax, long long n,
-                                                      int32_t* __restrict__ tri, float* __restrict__ t, float* __restrict__ uv,
-                                                      int* __restrict__ fb_count, int* __restrict__ fb_list, TraceCounters* __restrict__ counters) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(B2PT_TRACE_BLOCK) k_closest_octet(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
+                                                                    const float* __restrict__ tmax, long long n,
+                                                                    int32_t* __restrict__ tri, float* __restrict__ t, float* __restrict__ uv,
+                                                                    unsigned long long* __restrict__ next_ray,
+                                                                    int* __restrict__ fb_count, int* __restrict__ fb_list,
+                                                                    TraceCounters* __restrict__ counters) {
+    __shared__ uint2 stacks[B2PT_OCTETS_PER_BLOCK * B2PT_STACK_PITCH];
+    OctetCtx g = make_octet(stacks);
     unsigned n_nodes = 0, n_tris = 0;
-    if (i < n) {
-        RayQ r = load_ray(o, d, tmax, i);
-        HitRec h;
-        bool ok = closest_fast<COUNT>(S, r, h, n_nodes, n_tris);
-        store_hit(h, i, tri, t, uv);
-        if (!ok) fb_list[atomicAdd(fb_count, 1)] = (int)i;
+    while (true) {
+        unsigned long long base = 0;
+        if (g.gl == 0) base = atomicAdd(next_ray, (unsigned long long)B2PT_RAY_BATCH);
+        base = __shfl_sync(g.gmask, base, g.gbase);
+        if ((long long)base >= n) break;
+        long long end = min((long long)base + B2PT_RAY_BATCH, n);
+        for (long long i = (long long)base; i < end; ++i) {
+            RayQ r = load_ray(o, d, tmax, i);
+            HitRec h;
+            bool ok = closest_octet<COUNT>(S, g, r, h, n_nodes, n_tris);
+            if (g.gl == 0) {
+                store_hit(h, i, tri, t, uv);
+                if (!ok) fb_list[atomicAdd(fb_count, 1)] = (int)i;
+            }
+        }
     }
-    if (COUNT) flush_counters(counters, n_nodes, n_tris);
+    if (COUNT) { __syncwarp(); flush_counters(counters, n_nodes, n_tris); }
 }
 
 // Exact reference recursion over an index list (fallback) or over the whole batch (list == nullptr).
@@ -71,14 +89,107 @@ __global__ void __launch_bounds__(128) k_closest_exact(DeviceScene S, const floa
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_any_fast(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
-                                                  const float* __restrict__ tmax, long long n, uint8_t* __restrict__ occ,
-                                                  TraceCounters* __restrict__ counters) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(B2PT_TRACE_BLOCK) k_any_octet(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
+                                                                const float* __restrict__ tmax, long long n, uint8_t* __restrict__ occ,
+                                                                unsigned long long* __restrict__ next_ray, TraceCounters* __restrict__ counters) {
+    __shared__ uint2 stacks[B2PT_OCTETS_PER_BLOCK * B2PT_STACK_PITCH];
+    OctetCtx g = make_octet(stacks);
     unsigned n_nodes = 0, n_tris = 0;
-    if (i < n) {
-        RayQ r = load_ray(o, d, tmax, i);
-        occ[i] = any_fast<COUNT>(S, r, n_nodes, n_tris) ? 1 : 0;
+    while (true) {
+        unsigned long long base = 0;
+        if (g.gl == 0) base = atomicAdd(next_ray, (unsigned long long)B2PT_RAY_BATCH);
+        base = __shfl_sync(g.gmask, base, g.gbase);
+        if ((long long)base >= n) break;
+        long long end = min((long long)base + B2PT_RAY_BATCH, n);
+        for (long long i = (long long)base; i < end; ++i) {
+            RayQ r = load_ray(o, d, tmax, i);
+            int res = any_octet<COUNT>(S, g, r, n_nodes, n_tris);
+            if (res < 0) {   // stack overflow (cannot happen below 2^28 triangles): the exact recursion decides
+                HitRec h;
+                closest_exact_dfs(S, r, h);
+                res = h.tri >= 0;
+            }
+            if (g.gl == 0) occ[i] = (uint8_t)res;
+        }
+    }
+    if (COUNT) { __syncwarp(); flush_counters(counters, n_nodes, n_tris); }
+}
+
+
+// ---- one ray per lane, persistent warps with lane refill ------------------------------------------------
+#define B2PT_POOL_CHUNK 256     // ray indices a warp claims per global atomic
+#define B2PT_REFILL_MIN 4       // refill as soon as this many lanes are idle
+#define B2PT_TPS 2              // triangles per step
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_closest_thread(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
+                                                        const float* __restrict__ tmax, long long n,
+                                                        int32_t* __restrict__ tri, float* __restrict__ t, float* __restrict__ uv,
+                                                        unsigned long long* __restrict__ next_ray,
+                                                        int* __restrict__ fb_count, int* __restrict__ fb_list,
+                                                        TraceCounters* __restrict__ counters) {
+    LaneState st;
+    WarpPool pool{0, 0, false};
+    long long idx = -1;
+    unsigned n_nodes = 0, n_tris = 0;
+    if (S.nwide == 0) {   // empty scene: everything misses
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            HitRec h{B2PT_INF, -1, 0.0f, 0.0f};
+            store_hit(h, i, tri, t, uv);
+        }
+        return;
+    }
+    while (true) {
+        unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
+        if (idle && (__popc(idle) >= B2PT_REFILL_MIN || idle == 0xffffffffu)) {
+            long long got = warp_pool_take<B2PT_POOL_CHUNK>(pool, next_ray, n, idx < 0);
+            if (idx < 0 && got >= 0) {
+                idx = got;
+                lane_begin(st, load_ray(o, d, tmax, idx));
+            }
+            if (__ballot_sync(0xffffffffu, idx >= 0) == 0) break;   // nothing left anywhere
+        }
+        if (idx >= 0) {
+            if (lane_closest_step<COUNT, B2PT_TPS>(S, st, n_nodes, n_tris)) {
+                store_hit(st.best, idx, tri, t, uv);
+                if (!lane_certify(S, st)) fb_list[atomicAdd(fb_count, 1)] = (int)idx;
+                idx = -1;
+            }
+        }
+    }
+    if (COUNT) flush_counters(counters, n_nodes, n_tris);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_any_thread(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
+                                                    const float* __restrict__ tmax, long long n, uint8_t* __restrict__ occ,
+                                                    unsigned long long* __restrict__ next_ray, TraceCounters* __restrict__ counters) {
+    LaneState st;
+    WarpPool pool{0, 0, false};
+    long long idx = -1;
+    unsigned n_nodes = 0, n_tris = 0;
+    if (S.nwide == 0) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) occ[i] = 0;
+        return;
+    }
+    while (true) {
+        unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
+        if (idle && (__popc(idle) >= B2PT_REFILL_MIN || idle == 0xffffffffu)) {
+            long long got = warp_pool_take<B2PT_POOL_CHUNK>(pool, next_ray, n, idx < 0);
+            if (idx < 0 && got >= 0) {
+                idx = got;
+                lane_begin(st, load_ray(o, d, tmax, idx));
+            }
+            if (__ballot_sync(0xffffffffu, idx >= 0) == 0) break;
+        }
+        if (idx >= 0) {
+            int res = lane_any_step<COUNT, B2PT_TPS>(S, st, n_nodes, n_tris);
+            if (res) {
+                if (res == 3) { HitRec h; closest_exact_dfs(S, st.r, h); res = h.tri >= 0 ? 1 : 2; }
+                occ[idx] = res == 1 ? 1 : 0;
+                idx = -1;
+            }
+        }
     }
     if (COUNT) flush_counters(counters, n_nodes, n_tris);
 }
@@ -89,29 +200,39 @@ int launch_trace_closest(b2pt_ctx* ctx, const float* d_o, const float* d_d, cons
                          int32_t* d_tri, float* d_t, float* d_uv) {
     if (n <= 0) return B2PT_OK;
     cudaStream_t st = ctx->stream;
-    const int B = 128;
+    const int B = B2PT_TRACE_BLOCK;
     // Rays are processed in launches of at most 2^30 so the int fallback list can index them.
     const int64_t chunk = 1ll << 30;
+    unsigned long long* next_ray = reinterpret_cast<unsigned long long*>(ctx->d_fallback_count + 2);
     for (int64_t off = 0; off < n; off += chunk) {
         int64_t m = std::min(chunk, n - off);
         const float* o = d_o + 3 * off; const float* d = d_d + 3 * off;
         const float* tm = d_tmax ? d_tmax + off : nullptr;
         int32_t* tri = d_tri + off; float* t = d_t ? d_t + off : nullptr; float* uv = d_uv ? d_uv + 2 * off : nullptr;
         if (ctx->flags & B2PT_FLAG_EXACT_ONLY) {
-            int grid = (int)std::min<int64_t>((m + B - 1) / B, (int64_t)ctx->sm_count * 64);
-            k_closest_exact<<<grid, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, nullptr, nullptr, ctx->d_counters);
+            int grid = (int)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * 64);
+            k_closest_exact<<<grid, 128, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, nullptr, nullptr, ctx->d_counters);
             ctx->stats.kernel_launches += 1;
         } else {
             void* fb = nullptr;
             int rc = scratch_reserve(ctx, 0, sizeof(int) * (size_t)m, &fb);
             if (rc) return rc;
-            B2PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fallback_count, 0, sizeof(int), st));
-            unsigned grid = (unsigned)((m + B - 1) / B);
-            if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
-                k_closest_fast<true><<<grid, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
-            else
-                k_closest_fast<false><<<grid, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
-            k_closest_exact<<<ctx->sm_count * 8, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, ctx->d_fallback_count, (const int*)fb, ctx->d_counters);
+            B2PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fallback_count, 0, 64, st));
+            int64_t octets = (m + B2PT_RAY_BATCH - 1) / B2PT_RAY_BATCH;
+            unsigned grid = (unsigned)std::min<int64_t>((octets + B2PT_OCTETS_PER_BLOCK - 1) / B2PT_OCTETS_PER_BLOCK, (int64_t)ctx->sm_count * 16);
+            if (ctx->flags & B2PT_FLAG_OCTET) {
+                if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
+                    k_closest_octet<true><<<grid, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
+                else
+                    k_closest_octet<false><<<grid, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
+            } else {
+                unsigned tgrid = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * 12);
+                if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
+                    k_closest_thread<true><<<tgrid, 128, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
+                else
+                    k_closest_thread<false><<<tgrid, 128, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
+            }
+            k_closest_exact<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, ctx->d_fallback_count, (const int*)fb, ctx->d_counters);
             ctx->stats.kernel_launches += 2;
         }
         B2PT_CUDA(ctx, cudaGetLastError());
@@ -121,16 +242,27 @@ int launch_trace_closest(b2pt_ctx* ctx, const float* d_o, const float* d_d, cons
 
 int launch_trace_any(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n, uint8_t* d_occ) {
     if (n <= 0) return B2PT_OK;
-    const int B = 128;
+    const int B = B2PT_TRACE_BLOCK;
     const int64_t chunk = 1ll << 30;
+    unsigned long long* next_ray = reinterpret_cast<unsigned long long*>(ctx->d_fallback_count + 2);
     for (int64_t off = 0; off < n; off += chunk) {
         int64_t m = std::min(chunk, n - off);
-        unsigned grid = (unsigned)((m + B - 1) / B);
         const float* tm = d_tmax ? d_tmax + off : nullptr;
-        if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
-            k_any_fast<true><<<grid, B, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, ctx->d_counters);
-        else
-            k_any_fast<false><<<grid, B, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, ctx->d_counters);
+        B2PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fallback_count, 0, 64, ctx->stream));
+        int64_t octets = (m + B2PT_RAY_BATCH - 1) / B2PT_RAY_BATCH;
+        unsigned grid = (unsigned)std::min<int64_t>((octets + B2PT_OCTETS_PER_BLOCK - 1) / B2PT_OCTETS_PER_BLOCK, (int64_t)ctx->sm_count * 16);
+        if (ctx->flags & B2PT_FLAG_OCTET) {
+            if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
+                k_any_octet<true><<<grid, B, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
+            else
+                k_any_octet<false><<<grid, B, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
+        } else {
+            unsigned tgrid = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * 12);
+            if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
+                k_any_thread<true><<<tgrid, 128, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
+            else
+                k_any_thread<false><<<tgrid, 128, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
+        }
         ctx->stats.kernel_launches += 1;
         B2PT_CUDA(ctx, cudaGetLastError());
     }

@@ -6,10 +6,11 @@
 //                      implicit reference tree, global tMax shrink, reference tie rules.  Slow
 //                      (no ordering, binary tree) but exact by construction; used for the rays the
 //                      fast kernel cannot certify, and alone under B2PT_FLAG_EXACT_ONLY.
-//   closest_fast       ordered traversal of the 8-wide collapse.  Returns the candidate plus a
-//                      "certified" verdict: certified results are
-//                      provably what the reference returns; the rest go to closest_exact_dfs.
-//   any_fast           boolean occlusion query (shadow rays, renderer.hpp:274-278), exact without
+//   closest_octet      ordered, warp-cooperative (8 lanes per ray) traversal of the 8-wide collapse.
+//                      Returns the candidate plus a "certified" verdict: certified
+//                      results are provably what the reference returns; the rest go to
+//                      closest_exact_dfs.
+//   any_octet          boolean occlusion query (shadow rays, renderer.hpp:274-278), exact without
 //                      any fallback because its answer does not depend on traversal history.
 #pragma once
 #include "ctx.cuh"
@@ -86,142 +87,187 @@ __device__ __forceinline__ void closest_exact_dfs(const DeviceScene& S, const Ra
     }
 }
 
-// ---- fast ordered traversal of the wide BVH --------------------------------------------------------
-// Candidate set: triangles whose reference leaf box passes the reference slab test at T0 (exact —
-// the leaf's box is the wide child's box, tested with the reference arithmetic) and that
-// Triangle::intersect accepts in [tMin, T0].  Subtrees are culled when their box fails at T0 (exact,
-// monotone) or when their entry distance exceeds the current best by more than a relative 2^-10.
-// Returns true when the result is certified to be the reference's answer:
-//   * miss (no candidate), or
-//   * a unique minimum-t candidate whose leaf box still passes the slab test at T = t.
+// =====================================================================================================
+// Warp-cooperative traversal: 8 lanes ("an octet") per ray.
+//
+// The per-thread routines above execute with ~4 of 32 lanes active (ncu: profiles/r01_ncu_closest_v1_*):
+// every lane walks its own tree, so node steps, leaf steps, sorting and popping all diverge.  Here a ray
+// is owned by 8 consecutive lanes that always do the same thing: in a wide node each lane slab-tests ONE
+// child box (a coalesced 32-byte read per plane), in a reference leaf each lane runs Möller–Trumbore on
+// ONE triangle (leaves hold <= 8).  Hit ordering, stack pushes and the closest-hit reduction are
+// __ballot_sync / __shfl_sync operations inside the octet; the traversal stack is one shared-memory array
+// per octet.  The four octets of a warp are independent rays (sub-warp masks), so divergence is only
+// "octet A is in a node while octet B is in a leaf".
+//
+// Closest hit — candidate set: triangles whose reference leaf box passes the reference slab test at T0
+// (exact: the leaf's box IS the wide child's box, tested with the reference arithmetic) and that
+// Triangle::intersect accepts in [tMin, T0].  Subtrees are culled when their box fails at T0 (exact and
+// monotone: a superset box passes whenever a leaf inside it passes) or when their entry distance exceeds
+// the current best by more than a relative 2^-10.  The result is CERTIFIED to be the reference's answer
+// when it is a miss (no candidate), or a unique minimum-t candidate whose leaf box still passes the slab
+// test at T = t; everything else is re-run by closest_exact_dfs.
+//
+// Occlusion (renderer.hpp:274-278 asks only whether Scene::intersect returns true): before the first
+// accepted triangle ray.tMax still has its initial value, so the answer is "does a triangle exist whose
+// reference leaf box passes at T0 and which Triangle::intersect accepts in [tMin, T0]" — independent of
+// traversal order, exact without any fallback.
+// =====================================================================================================
+#define B2PT_STACK 64            // entries per octet; deepest push chain is 7 per wide level, <= 9 levels
+#define B2PT_STACK_PITCH 65      // +1 entry of padding: octets' stacks start in different banks
+
+struct OctetCtx {
+    unsigned gmask;      // the octet's 8 lanes within the warp
+    int gl;              // lane within the octet, 0..7
+    int gbase;           // first lane of the octet within the warp
+    uint2* stack;        // shared-memory stack of this octet
+};
+
+__device__ __forceinline__ OctetCtx make_octet(uint2* block_stacks) {
+    OctetCtx c;
+    int lane = threadIdx.x & 31;
+    c.gl = lane & 7;
+    c.gbase = lane & ~7;
+    c.gmask = 0xffu << c.gbase;
+    c.stack = block_stacks + (threadIdx.x >> 3) * B2PT_STACK_PITCH;
+    return c;
+}
+
+// One lane's slab test of child `gl` of a wide node.
+__device__ __forceinline__ bool octet_child_test(const WideNode* nd, int gl, const RayQ& r, float& tmin, uint32_t& code) {
+    float lx = __ldg(&nd->lox[gl]), ly = __ldg(&nd->loy[gl]), lz = __ldg(&nd->loz[gl]);
+    float hx = __ldg(&nd->hix[gl]), hy = __ldg(&nd->hiy[gl]), hz = __ldg(&nd->hiz[gl]);
+    code = __ldg(&nd->child[gl]);
+    float tmax = r.T0;
+    tmin = B2PT_TMIN;
+    slab_axis(lx, hx, r.o.x, r.invD.x, tmin, tmax);
+    slab_axis(ly, hy, r.o.y, r.invD.y, tmin, tmax);
+    slab_axis(lz, hz, r.o.z, r.invD.z, tmin, tmax);
+    return tmax > tmin;
+}
+
+// Closest hit, cooperative.  All 8 lanes of the octet call this with the same ray and get the same result.
+// Returns the certificate (true = provably the reference's answer).
 template <bool COUNT>
-__device__ __forceinline__ bool closest_fast(const DeviceScene& S, const RayQ& r, HitRec& out,
-                                             unsigned& n_nodes, unsigned& n_tris) {
+__device__ __forceinline__ bool closest_octet(const DeviceScene& S, const OctetCtx& g, const RayQ& r, HitRec& out,
+                                              unsigned& n_nodes, unsigned& n_tris) {
     out.t = B2PT_INF; out.tri = -1; out.u = 0.0f; out.v = 0.0f;
     if (S.nwide == 0) return true;
-    bool tie = false;
-    float best = B2PT_INF;        // t of the current best candidate
-    float cull = r.T0;            // entry distances above this cannot matter
-    // stack of (child code, entry)
-    uint32_t scode[96];
-    float sent[96];
+    bool tie = false, overflow = false;
+    float cull = r.T0;
     int sp = 0;
-    uint32_t cur = 0;             // root wide node
+    uint32_t cur = 0;
     while (true) {
         if (!(cur & B2PT_CHILD_LEAF)) {
-            const WideNode* nd = &S.wide[cur];
-            if (COUNT) ++n_nodes;
-            // 8 children, SoA: 16-byte loads
-            float lox[8], loy[8], loz[8], hix[8], hiy[8], hiz[8];
-            uint32_t code[8];
-            {
-                const float4* p = reinterpret_cast<const float4*>(nd);
+            if (COUNT && g.gl == 0) ++n_nodes;
+            float tmin; uint32_t code;
+            bool hit = octet_child_test(&S.wide[cur], g.gl, r, tmin, code) && tmin <= cull;
+            unsigned hm = (__ballot_sync(g.gmask, hit) >> g.gbase) & 0xffu;
+            int n = __popc(hm);
+            if (n > 0) {
+                // rank = number of hit children that must sit BELOW me on the stack (farther first)
+                int rank = 0;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    float4 a = __ldg(p + 0 + k), b = __ldg(p + 2 + k), c = __ldg(p + 4 + k);
-                    float4 d = __ldg(p + 6 + k), e = __ldg(p + 8 + k), f = __ldg(p + 10 + k);
-                    lox[4 * k] = a.x; lox[4 * k + 1] = a.y; lox[4 * k + 2] = a.z; lox[4 * k + 3] = a.w;
-                    loy[4 * k] = b.x; loy[4 * k + 1] = b.y; loy[4 * k + 2] = b.z; loy[4 * k + 3] = b.w;
-                    loz[4 * k] = c.x; loz[4 * k + 1] = c.y; loz[4 * k + 2] = c.z; loz[4 * k + 3] = c.w;
-                    hix[4 * k] = d.x; hix[4 * k + 1] = d.y; hix[4 * k + 2] = d.z; hix[4 * k + 3] = d.w;
-                    hiy[4 * k] = e.x; hiy[4 * k + 1] = e.y; hiy[4 * k + 2] = e.z; hiy[4 * k + 3] = e.w;
-                    hiz[4 * k] = f.x; hiz[4 * k + 1] = f.y; hiz[4 * k + 2] = f.z; hiz[4 * k + 3] = f.w;
+                for (int j = 0; j < 8; ++j) {
+                    float tj = __shfl_sync(g.gmask, tmin, g.gbase + j);
+                    bool below = (tj > tmin) || (tj == tmin && j < g.gl);
+                    rank += (((hm >> j) & 1u) && below) ? 1 : 0;
                 }
-                const uint4* q = reinterpret_cast<const uint4*>(nd->child);
-                uint4 c0 = __ldg(q), c1 = __ldg(q + 1);
-                code[0] = c0.x; code[1] = c0.y; code[2] = c0.z; code[3] = c0.w;
-                code[4] = c1.x; code[5] = c1.y; code[6] = c1.z; code[7] = c1.w;
-            }
-            // test all 8, push hits in insertion-sorted order (farthest deepest)
-            int base = sp;
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                float tmin = B2PT_TMIN, tmax = r.T0;
-                slab_axis(lox[s], hix[s], r.o.x, r.invD.x, tmin, tmax);
-                slab_axis(loy[s], hiy[s], r.o.y, r.invD.y, tmin, tmax);
-                slab_axis(loz[s], hiz[s], r.o.z, r.invD.z, tmin, tmax);
-                if (tmax > tmin && tmin <= cull) {
-                    // insert so that entries in [base, sp) are sorted by decreasing entry distance
-                    int j = sp++;
-                    while (j > base && sent[j - 1] < tmin) { sent[j] = sent[j - 1]; scode[j] = scode[j - 1]; --j; }
-                    sent[j] = tmin; scode[j] = code[s];
-                }
+                if (sp + n - 1 > B2PT_STACK) { overflow = true; break; }
+                if (hit && rank < n - 1) g.stack[sp + rank] = make_uint2(code, __float_as_uint(tmin));
+                // the nearest child (rank n-1) is visited next without going through the stack
+                unsigned nm = (__ballot_sync(g.gmask, hit && rank == n - 1) >> g.gbase) & 0xffu;
+                cur = __shfl_sync(g.gmask, code, g.gbase + __ffs(nm) - 1);
+                sp += n - 1;
+                __syncwarp(g.gmask);
+                continue;
             }
         } else {
-            // reference leaf: its box passed at T0, so its triangles are candidates
             int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;
-            for (int i = first; i < first + cnt; ++i) {
-                float t, u, v;
+            float t = B2PT_INF, u = 0.0f, v = 0.0f;
+            bool acc = false;
+            if (g.gl < cnt) {
                 if (COUNT) ++n_tris;
-                if (tri_fetch_test(S, i, r, r.T0, t, u, v)) {
-                    if (t < best) {
-                        best = t; out.t = t; out.tri = i; out.u = u; out.v = v; tie = false;
-                        cull = fminf(r.T0, __fmaf_rn(t, 0.0009765625f, t));
-                    } else if (t == best) {
-                        tie = true;
-                    }
+                acc = tri_fetch_test(S, first + g.gl, r, r.T0, t, u, v);
+                if (!acc) t = B2PT_INF;
+            }
+            unsigned am = (__ballot_sync(g.gmask, acc) >> g.gbase) & 0xffu;
+            if (am) {
+                // octet minimum of t
+                float m = t;
+                m = fminf(m, __shfl_xor_sync(g.gmask, m, 1));
+                m = fminf(m, __shfl_xor_sync(g.gmask, m, 2));
+                m = fminf(m, __shfl_xor_sync(g.gmask, m, 4));
+                unsigned wm = (__ballot_sync(g.gmask, acc && t == m) >> g.gbase) & 0xffu;
+                if (m < out.t) {
+                    int w = __ffs(wm) - 1;   // first triangle of the leaf with the minimum t (bvh.hpp:88)
+                    out.t = m;
+                    out.tri = first + w;
+                    out.u = __shfl_sync(g.gmask, u, g.gbase + w);
+                    out.v = __shfl_sync(g.gmask, v, g.gbase + w);
+                    tie = __popc(wm) > 1;
+                    cull = fminf(r.T0, __fmaf_rn(m, 0.0009765625f, m));
+                } else if (m == out.t) {
+                    tie = true;
                 }
             }
         }
-        // pop
+        // pop the nearest pending subtree that can still matter
         bool got = false;
         while (sp > 0) {
             --sp;
-            if (sent[sp] <= cull) { cur = scode[sp]; got = true; break; }
+            uint2 e = g.stack[sp];
+            if (__uint_as_float(e.y) <= cull) { cur = e.x; got = true; break; }
         }
         if (!got) break;
     }
+    if (overflow) return false;
     if (out.tri < 0) return true;
     if (tie) return false;
-    // certify: the winner's reference leaf must still be visible with ray.tMax == t
     int leaf = __float_as_int(__ldg(&S.tri[3ll * out.tri]).w);
     float entry;
     return box_pass(__ldg(&S.leaf_lo[leaf]), __ldg(&S.leaf_hi[leaf]), r, out.t, entry);
 }
 
-// ---- occlusion query -------------------------------------------------------------------------------
-// renderer.hpp:274-278 asks only whether Scene::intersect returns true.  Before the first accepted
-// triangle ray.tMax still has its initial value, so the answer is: does any triangle exist whose
-// reference leaf box passes the slab test at T0 and which Triangle::intersect accepts in [tMin, T0].
+// Occlusion query, cooperative.  Returns 1 occluded, 0 free, -1 stack overflow (caller must use the exact path).
 template <bool COUNT>
-__device__ __forceinline__ bool any_fast(const DeviceScene& S, const RayQ& r, unsigned& n_nodes, unsigned& n_tris) {
-    if (S.nwide == 0) return false;
-    uint32_t scode[96];
+__device__ __forceinline__ int any_octet(const DeviceScene& S, const OctetCtx& g, const RayQ& r, unsigned& n_nodes, unsigned& n_tris) {
+    if (S.nwide == 0) return 0;
     int sp = 0;
     uint32_t cur = 0;
     while (true) {
         if (!(cur & B2PT_CHILD_LEAF)) {
-            const WideNode* nd = &S.wide[cur];
-            if (COUNT) ++n_nodes;
-            const float4* p = reinterpret_cast<const float4*>(nd);
-            const uint4* q = reinterpret_cast<const uint4*>(nd->child);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                float4 a = __ldg(p + 0 + k), b = __ldg(p + 2 + k), c = __ldg(p + 4 + k);
-                float4 d = __ldg(p + 6 + k), e = __ldg(p + 8 + k), f = __ldg(p + 10 + k);
-                uint4 cc = __ldg(q + k);
-                const float lx[4] = {a.x, a.y, a.z, a.w}, ly[4] = {b.x, b.y, b.z, b.w}, lz[4] = {c.x, c.y, c.z, c.w};
-                const float hx[4] = {d.x, d.y, d.z, d.w}, hy[4] = {e.x, e.y, e.z, e.w}, hz[4] = {f.x, f.y, f.z, f.w};
-                const uint32_t cd[4] = {cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    float tmin = B2PT_TMIN, tmax = r.T0;
-                    slab_axis(lx[s], hx[s], r.o.x, r.invD.x, tmin, tmax);
-                    slab_axis(ly[s], hy[s], r.o.y, r.invD.y, tmin, tmax);
-                    slab_axis(lz[s], hz[s], r.o.z, r.invD.z, tmin, tmax);
-                    if (tmax > tmin) scode[sp++] = cd[s];
-                }
+            if (COUNT && g.gl == 0) ++n_nodes;
+            float tmin; uint32_t code;
+            bool hit = octet_child_test(&S.wide[cur], g.gl, r, tmin, code);
+            unsigned hm = (__ballot_sync(g.gmask, hit) >> g.gbase) & 0xffu;
+            int n = __popc(hm);
+            if (n > 0) {
+                if (sp + n - 1 > B2PT_STACK) return -1;
+                // leaves first: they can end the query at once (top of stack = visited next)
+                bool leaf = (code & B2PT_CHILD_LEAF) != 0;
+                unsigned lm = (__ballot_sync(g.gmask, hit && leaf) >> g.gbase) & 0xffu;
+                unsigned below_me = (1u << g.gl) - 1u;
+                int nl = __popc(lm);
+                int pos = leaf ? (n - nl) + __popc(lm & below_me) : __popc((hm & ~lm) & below_me);
+                if (hit && pos < n - 1) g.stack[sp + pos] = make_uint2(code, 0u);
+                unsigned nm = (__ballot_sync(g.gmask, hit && pos == n - 1) >> g.gbase) & 0xffu;
+                cur = __shfl_sync(g.gmask, code, g.gbase + __ffs(nm) - 1);
+                sp += n - 1;
+                __syncwarp(g.gmask);
+                continue;
             }
         } else {
             int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;
-            for (int i = first; i < first + cnt; ++i) {
+            bool acc = false;
+            if (g.gl < cnt) {
                 float t, u, v;
                 if (COUNT) ++n_tris;
-                if (tri_fetch_test(S, i, r, r.T0, t, u, v)) return true;
+                acc = tri_fetch_test(S, first + g.gl, r, r.T0, t, u, v);
             }
+            if (__ballot_sync(g.gmask, acc) & g.gmask) return 1;
         }
-        if (sp == 0) return false;
-        cur = scode[--sp];
+        if (sp == 0) return 0;
+        cur = g.stack[--sp].x;
     }
 }
 

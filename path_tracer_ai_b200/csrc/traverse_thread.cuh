@@ -1,0 +1,190 @@
+// traverse_thread.cuh — one-ray-per-lane traversal of the wide BVH as a RESUMABLE state machine, for
+// persistent kernels that refill finished lanes with new rays.
+//
+// ncu on the first (run-to-completion, one thread per ray) kernel showed 4.3 of 32 lanes active per
+// instruction (profiles/r01_ncu_closest_v1_perthread.txt).  Two causes multiply: lanes whose ray has
+// finished idle until the slowest ray of the warp ends (no refill), and a lane in a leaf (8 triangle
+// tests) serialises against lanes in a node (8 box tests).  Here a lane advances its ray by ONE bounded
+// step per loop iteration — one wide node, or up to TPS triangles of the current leaf — and the kernel
+// loop refills idle lanes from a warp-local pool of ray indices between steps.
+//
+// Exactness is that of DESIGN.md §2: same candidate set, same certificate as the cooperative variant.
+#pragma once
+#include "traverse.cuh"
+
+namespace b2pt {
+
+#define B2PT_TSTACK 64   // 7 pushes per wide level, <= 9 levels below 2^28 triangles
+
+struct LaneState {
+    RayQ r;
+    HitRec best;
+    float cull;
+    int sp;
+    uint32_t cur;          // inner wide node to expand (valid when tri_next == tri_end)
+    int tri_next, tri_end; // triangles of the current leaf still to test
+    bool tie;
+    bool overflow;
+    uint2 stack[B2PT_TSTACK];   // (child code, entry distance bits)
+};
+
+__device__ __forceinline__ void lane_begin(LaneState& st, const RayQ& r) {
+    st.r = r;
+    st.best.t = B2PT_INF; st.best.tri = -1; st.best.u = 0.0f; st.best.v = 0.0f;
+    st.cull = r.T0;
+    st.sp = 0;
+    st.cur = 0;
+    st.tri_next = st.tri_end = 0;
+    st.tie = false;
+    st.overflow = false;
+}
+
+// Expands wide node st.cur: slab-tests the 8 children at T0 and pushes the survivors sorted by entry
+// distance (farthest deepest).  ANY = occlusion query: no ordering, no distance culling.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void lane_node_step(const DeviceScene& S, LaneState& st, unsigned& n_nodes) {
+    const WideNode* nd = &S.wide[st.cur];
+    if (COUNT) ++n_nodes;
+    const float4* p = reinterpret_cast<const float4*>(nd);
+    const uint4* q = reinterpret_cast<const uint4*>(nd->child);
+    if (st.sp + 8 > B2PT_TSTACK) { st.overflow = true; return; }
+    const int base = st.sp;
+    int sp = st.sp;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float4 a = __ldg(p + 0 + k), b = __ldg(p + 2 + k), c = __ldg(p + 4 + k);
+        float4 d = __ldg(p + 6 + k), e = __ldg(p + 8 + k), f = __ldg(p + 10 + k);
+        uint4 cc = __ldg(q + k);
+        const float lx[4] = {a.x, a.y, a.z, a.w}, ly[4] = {b.x, b.y, b.z, b.w}, lz[4] = {c.x, c.y, c.z, c.w};
+        const float hx[4] = {d.x, d.y, d.z, d.w}, hy[4] = {e.x, e.y, e.z, e.w}, hz[4] = {f.x, f.y, f.z, f.w};
+        const uint32_t cd[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            float tmin = B2PT_TMIN, tmax = st.r.T0;
+            slab_axis(lx[s], hx[s], st.r.o.x, st.r.invD.x, tmin, tmax);
+            slab_axis(ly[s], hy[s], st.r.o.y, st.r.invD.y, tmin, tmax);
+            slab_axis(lz[s], hz[s], st.r.o.z, st.r.invD.z, tmin, tmax);
+            if (ANY) {
+                if (tmax > tmin) st.stack[sp++] = make_uint2(cd[s], 0u);
+            } else if (tmax > tmin && tmin <= st.cull) {
+                int j = sp++;
+                while (j > base && __uint_as_float(st.stack[j - 1].y) < tmin) { st.stack[j] = st.stack[j - 1]; --j; }
+                st.stack[j] = make_uint2(cd[s], __float_as_uint(tmin));
+            }
+        }
+    }
+    st.sp = sp;
+}
+
+// Pops the next subtree that can still matter.  Returns false when the stack is exhausted.
+template <bool ANY>
+__device__ __forceinline__ bool lane_pop(LaneState& st) {
+    while (st.sp > 0) {
+        uint2 e = st.stack[--st.sp];
+        if (ANY || __uint_as_float(e.y) <= st.cull) {
+            if (e.x & B2PT_CHILD_LEAF) {
+                st.tri_next = e.x & 0x0FFFFFFF;
+                st.tri_end = st.tri_next + (int)((e.x >> 28) & 7) + 1;
+            } else {
+                st.cur = e.x;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+// One bounded step of a closest-hit query.  Returns true when the traversal is finished.
+template <bool COUNT, int TPS>
+__device__ __forceinline__ bool lane_closest_step(const DeviceScene& S, LaneState& st, unsigned& n_nodes, unsigned& n_tris) {
+    if (st.tri_next < st.tri_end) {
+#pragma unroll
+        for (int k = 0; k < TPS; ++k) {
+            if (st.tri_next < st.tri_end) {
+                float t, u, v;
+                if (COUNT) ++n_tris;
+                int i = st.tri_next++;
+                if (tri_fetch_test(S, i, st.r, st.r.T0, t, u, v)) {
+                    if (t < st.best.t) {
+                        st.best.t = t; st.best.tri = i; st.best.u = u; st.best.v = v; st.tie = false;
+                        st.cull = fminf(st.r.T0, __fmaf_rn(t, 0.0009765625f, t));
+                    } else if (t == st.best.t) {
+                        st.tie = true;
+                    }
+                }
+            }
+        }
+        if (st.tri_next < st.tri_end) return false;
+    } else {
+        lane_node_step<false, COUNT>(S, st, n_nodes);
+        if (st.overflow) return true;
+    }
+    return !lane_pop<false>(st);
+}
+
+// After lane_closest_step returned true: is the result certified to be the reference's answer?
+__device__ __forceinline__ bool lane_certify(const DeviceScene& S, const LaneState& st) {
+    if (st.overflow) return false;
+    if (st.best.tri < 0) return true;
+    if (st.tie) return false;
+    int leaf = __float_as_int(__ldg(&S.tri[3ll * st.best.tri]).w);
+    float entry;
+    return box_pass(__ldg(&S.leaf_lo[leaf]), __ldg(&S.leaf_hi[leaf]), st.r, st.best.t, entry);
+}
+
+// One bounded step of an occlusion query.  Returns 0 = keep going, 1 = finished & occluded, 2 = finished
+// & free, 3 = stack overflow (caller must use the exact recursion).
+template <bool COUNT, int TPS>
+__device__ __forceinline__ int lane_any_step(const DeviceScene& S, LaneState& st, unsigned& n_nodes, unsigned& n_tris) {
+    if (st.tri_next < st.tri_end) {
+#pragma unroll
+        for (int k = 0; k < TPS; ++k) {
+            if (st.tri_next < st.tri_end) {
+                float t, u, v;
+                if (COUNT) ++n_tris;
+                if (tri_fetch_test(S, st.tri_next++, st.r, st.r.T0, t, u, v)) return 1;
+            }
+        }
+        if (st.tri_next < st.tri_end) return 0;
+    } else {
+        lane_node_step<true, COUNT>(S, st, n_nodes);
+        if (st.overflow) return 3;
+    }
+    return lane_pop<true>(st) ? 0 : 2;
+}
+
+// Warp-local pool of work indices: the warp claims CHUNK indices per global atomic and hands them to idle
+// lanes by ballot rank.  All 32 lanes must call refill() together.
+struct WarpPool {
+    long long next, end;   // warp-uniform
+    bool exhausted;
+};
+
+template <int CHUNK>
+__device__ __forceinline__ long long warp_pool_take(WarpPool& pool, unsigned long long* counter, long long total, bool want) {
+    // returns a work index for lanes with want == true (or -1)
+    const int lane = threadIdx.x & 31;
+    long long mine = -1;
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        unsigned need = __ballot_sync(0xffffffffu, want && mine < 0);
+        if (need == 0) break;
+        if (pool.next >= pool.end) {
+            if (pool.exhausted) break;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)CHUNK);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            pool.next = (long long)base;
+            pool.end = min((long long)base + CHUNK, total);
+            if (pool.next >= total) { pool.exhausted = true; pool.next = pool.end = 0; break; }
+        }
+        long long avail = pool.end - pool.next;
+        int rank = __popc(need & ((1u << lane) - 1u));
+        if (want && mine < 0 && rank < avail) mine = pool.next + rank;
+        long long taken = min((long long)__popc(need), avail);
+        pool.next += taken;
+    }
+    return mine;
+}
+
+}  // namespace b2pt

@@ -19,6 +19,7 @@ ap.add_argument("--any", action="store_true")
 ap.add_argument("--soup", action="store_true", help="random triangle soup instead of the mesh scene")
 ap.add_argument("--coherent", action="store_true", help="camera-like primary rays instead of random rays")
 ap.add_argument("--out", default="")
+ap.add_argument("--flags", type=int, default=0)
 args = ap.parse_args()
 
 t0 = time.time()
@@ -31,7 +32,7 @@ t1 = time.time()
 order = pt.reference_order(ms["pos"])
 t2 = time.time()
 pos = ms["pos"][order]
-eng = pt.Engine()
+eng = pt.Engine(flags=args.flags)
 eng.upload_scene(pos, None if ms["nrm"] is None else ms["nrm"][order], None if ms["mat"] is None else ms["mat"][order], ms["materials8"])
 build_s = eng.stats()["build_seconds"]
 t3 = time.time()
@@ -68,7 +69,7 @@ if args.any:
 else:
     res["hit_frac"] = float((tri >= 0).float().mean())
 # instrumented counting build of the same kernel on the same BVH and a 1/8 sample of the batch
-ce = pt.Engine(flags=pt.FLAG_COUNT_FETCHES)
+ce = pt.Engine(flags=pt.FLAG_COUNT_FETCHES | args.flags)
 ce.upload_scene(pos)
 m = max(n // 8, 1)
 if args.any:
