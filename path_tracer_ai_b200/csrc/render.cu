@@ -5,13 +5,13 @@
 // One frame = pixel chunks x sample chunks of at most `max_paths` camera paths.  Per chunk:
 //   k_raygen                         camera rays (camera.hpp:18-29), T = 1, L = 0
 //   for depth in 0 .. maxBounces-1:
-//     k_extend (+ k_extend_fallback)  closest hit, warp-cooperative (8 lanes per ray, persistent octets)
+//     k_extend (+ k_extend_fallback)  closest hit: one ray per lane, persistent warps with lane refill
 //     k_hitinfo                       hit point, shading normal, material; bins the path into its material
 //                                     queue (1-pass counting sort on the material type) and into the
 //                                     direct-light queue
-//     k_direct                        one octet per (vertex, light): shadow ray, cooperative any-hit
-//                                     traversal, light contribution; a vertex's lights are summed in order
-//     k_shade<DIFFUSE|SPECULAR|DIELECTRIC>  L += T*direct, BSDF sample, T update, next ray -> next queue
+//     k_shadow                        one ray per (vertex, light): any-hit traversal -> visibility byte
+//     k_shade<DIFFUSE|SPECULAR|DIELECTRIC>  direct light from the visible lights (summed in light order),
+//                                     L += T*direct, BSDF sample, T update, next ray -> next queue
 //   k_resolve                        per pixel: samples added in sample order (renderer.hpp:69-72)
 // k_finalize divides by spp (renderer.hpp:75-81).
 //
@@ -22,8 +22,10 @@
 // (scene, camera, settings, seed), independent of chunking, queue order and GPU count.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
-#include "traverse.cuh"
+#include "traverse_rtc.cuh"
+#include "traverse_thread.cuh"
 
 namespace b2pt {
 
@@ -35,14 +37,14 @@ struct Wave {
     float4 *ro, *rd;       // ray origin / direction (direction already normalised by the Ray ctor rule)
     float4 *hit;           // closest hit of the current bounce: (t, tri id, u, v)
     float4 *g0, *g1;       // (P, material id) / (shading normal, 0)
-    float4 *direct;        // direct light at the current vertex
+    uint8_t *vis;          // per (path, light): 1 = shadow ray occluded
     float4 *thr, *rad;     // throughput T, radiance L
     int *q_active[2];      // active paths, ping-pong by depth parity
     int *q_mat[3];         // per-material queues
     int *q_shadow;         // vertices that need direct light (diffuse + specular)
     int *q_fallback;       // closest-hit queries the fast traversal could not certify
     int *counters;         // C_* above
-    unsigned long long* totals;   // [0] extend rays, [1] shadow rays, [2] fallback rays
+    unsigned long long* totals;   // [0] extend rays, [1] shadow rays, [2] fallback rays, [4] extend work pool, [5] shadow work pool
 };
 
 struct CamConst {
@@ -139,42 +141,106 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
     warp_append(&W.counters[C_SHADOW], W.q_shadow, e.shadow, p);
 }
 
-#define B2PT_WF_BLOCK 128
-#define B2PT_WF_OCTETS (B2PT_WF_BLOCK / 8)
-#define B2PT_WF_BATCH 8
+#define B2PT_WF_CHUNK 256   // queue entries a warp claims per global atomic
+#define B2PT_WF_REFILL 4    // idle lanes that trigger a refill
 
-// Closest hit for the active paths: persistent octets (8 lanes per ray) claim B2PT_WF_BATCH queue entries
-// per atomic.  Writes the hit record; uncertified rays go to the fallback queue.
-template <bool COUNT>
-__global__ void __launch_bounds__(B2PT_WF_BLOCK) k_extend(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
-                                                          int P, TraceCounters* __restrict__ tc) {
-    __shared__ uint2 stacks[B2PT_WF_OCTETS * B2PT_STACK_PITCH];
-    OctetCtx g = make_octet(stacks);
-    const int total = list ? *count_ptr : P;
+// Closest hit for the active paths: one ray per lane, persistent warps that refill idle lanes from a
+// warp-local pool of queue entries.  Writes the hit record; uncertified rays go to the fallback queue.
+template <bool COUNT, int TPS>
+__global__ void __launch_bounds__(B2PT_TBLOCK) k_extend(int refill_min, DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
+                                                        int P, TraceCounters* __restrict__ tc) {
+    __shared__ uint2 lane_stacks[B2PT_SSTACK * B2PT_TBLOCK];
+    LaneState st;
+    st.stack.sm = lane_stacks + threadIdx.x;
+    WarpPool pool{0, 0, false};
+    const long long total = list ? *count_ptr : P;
+    int p = -1;
     unsigned n_nodes = 0, n_tris = 0;
     while (true) {
-        int base = 0;
-        if (g.gl == 0) base = atomicAdd(&W.counters[C_NEXT], B2PT_WF_BATCH);
-        base = __shfl_sync(g.gmask, base, g.gbase);
-        if (base >= total) break;
-        int end = min(base + B2PT_WF_BATCH, total);
-        for (int k = base; k < end; ++k) {
-            int p = list ? list[k] : k;
-            float4 o4 = W.ro[p], d4 = W.rd[p];
-            RayQ r;
-            r.o = f4v(o4); r.d = f4v(d4);
-            r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
-            r.T0 = B2PT_INF;
-            HitRec h;
-            bool ok = closest_octet<COUNT>(S, g, r, h, n_nodes, n_tris);
-            if (g.gl == 0) {
-                W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
-                if (!ok) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
+        unsigned idle = __ballot_sync(0xffffffffu, p < 0);
+        if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+            long long got = warp_pool_take<B2PT_WF_CHUNK>(pool, &W.totals[4], total, p < 0);
+            if (p < 0 && got >= 0) {
+                p = list ? list[got] : (int)got;
+                float4 o4 = W.ro[p], d4 = W.rd[p];
+                RayQ r;
+                r.o = f4v(o4); r.d = f4v(d4);
+                r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
+                r.T0 = B2PT_INF;
+                lane_begin(st, r);
+                if (S.nwide == 0) { W.hit[p] = make_float4(B2PT_INF, __int_as_float(-1), 0.0f, 0.0f); p = -1; }
+            }
+            if (__ballot_sync(0xffffffffu, p >= 0) == 0 && pool.exhausted) break;
+        }
+        if (p >= 0) {
+            if (lane_closest_step<COUNT, TPS>(S, st, n_nodes, n_tris)) {
+                W.hit[p] = make_float4(st.best.t, __int_as_float(st.best.tri), st.best.u, st.best.v);
+                if (!lane_certify(S, st)) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
+                p = -1;
             }
         }
     }
     if (COUNT) {
-        __syncwarp();
+        for (int off = 16; off > 0; off >>= 1) {
+            n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+            n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
+    }
+}
+
+// Run-to-completion variants for coherent batches (traverse_rtc.cuh): one thread per queue entry.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend_rtc(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
+                                                    int P, TraceCounters* __restrict__ tc) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = list ? *count_ptr : P;
+    unsigned n_nodes = 0, n_tris = 0;
+    if (k < total) {
+        int p = list ? list[k] : k;
+        float4 o4 = W.ro[p], d4 = W.rd[p];
+        RayQ r;
+        r.o = f4v(o4); r.d = f4v(d4);
+        r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
+        r.T0 = B2PT_INF;
+        HitRec h;
+        bool ok = closest_rtc<COUNT>(S, r, h, n_nodes, n_tris);
+        W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+        if (!ok) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
+    }
+    if (COUNT) {
+        for (int off = 16; off > 0; off >>= 1) {
+            n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+            n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow_rtc(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
+    const int nl = S.nlight;
+    const long long nsh = W.counters[C_SHADOW];
+    const long long total = nsh * nl;
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n_nodes = 0, n_tris = 0;
+    if (j < total) {
+        int l = (int)(j / nsh), k = (int)(j - (long long)l * nsh);   // light-major
+        int p = W.q_shadow[k];
+        float4 g0 = W.g0[p], g1 = W.g1[p];
+        V3 P = f4v(g0), n = f4v(g1);
+        const DLight& lt = S.lights[l];
+        V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
+        float dist = vlength(lightDir);
+        uint8_t occ = 0;
+        if (!(dist < 0.0001f)) {
+            lightDir = vnormalize(lightDir);
+            RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));
+            occ = any_rtc<COUNT>(S, r, n_nodes, n_tris) ? 1 : 0;
+        }
+        W.vis[(long long)p * nl + l] = occ;
+    }
+    if (COUNT) {
         for (int off = 16; off > 0; off >>= 1) {
             n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
             n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
@@ -234,82 +300,84 @@ __device__ __forceinline__ float schlick_fresnel(float cosTheta, float F0) {
     return B2PT_ADD(F0, B2PT_MUL(B2PT_SUB(1.0f, F0), x5));
 }
 
-// calculateDirectLighting (renderer.hpp:252-301).  One octet (8 lanes) per (vertex, light): the octet builds
-// the shadow ray, runs the cooperative any-hit traversal and evaluates the light's contribution; GPV octets
-// of a warp share a vertex and their contributions are summed in light order (more than GPV lights: rounds).
-template <int GPV, bool COUNT>
-__global__ void __launch_bounds__(B2PT_WF_BLOCK) k_direct(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
-    __shared__ uint2 stacks[B2PT_WF_OCTETS * B2PT_STACK_PITCH];
-    OctetCtx g = make_octet(stacks);
-    const int total = W.counters[C_SHADOW];
-    const int lane = threadIdx.x & 31, octet = lane >> 3;
-    const int vslot = octet / GPV, lsub = octet % GPV;
-    constexpr int VPW = 4 / GPV;   // vertices per warp and iteration
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+// Shadow rays of calculateDirectLighting (renderer.hpp:271-278): one work item per (vertex, light), one ray per
+// lane, persistent warps with refill.  Writes vis[p * nlight + l] = 1 when Scene::intersect would return true.
+template <bool COUNT, int TPS>
+__global__ void __launch_bounds__(B2PT_TBLOCK) k_shadow(int refill_min, DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
+    __shared__ uint2 lane_stacks[B2PT_SSTACK * B2PT_TBLOCK];
+    LaneState st;
+    st.stack.sm = lane_stacks + threadIdx.x;
+    WarpPool pool{0, 0, false};
+    const int nl = S.nlight;
+    const long long total = (long long)W.counters[C_SHADOW] * nl;
+    long long slot = -1;   // index into vis of the ray this lane is tracing
     unsigned n_nodes = 0, n_tris = 0;
-    for (int vbase = warp * VPW; vbase < total; vbase += nwarps * VPW) {
-        const int k = vbase + vslot;
-        const bool live = k < total;
-        int p = 0;
-        V3 P = mk3(0, 0, 0), n = mk3(0, 0, 0), viewDir = mk3(0, 0, 0);
-        DMaterial m{};
-        if (live) {
-            p = W.q_shadow[k];
-            float4 g0 = W.g0[p], g1 = W.g1[p], d4 = W.rd[p];
-            P = f4v(g0); n = f4v(g1); viewDir = vneg(f4v(d4));
-            m = S.mats[__float_as_int(g0.w)];
-        }
-        float tx = 0.0f, ty = 0.0f, tz = 0.0f;
-        for (int l0 = 0; l0 < S.nlight; l0 += GPV) {
-            const int l = l0 + lsub;
-            float cx = 0.0f, cy = 0.0f, cz = 0.0f;
-            int addf = 0;
-            if (live && l < S.nlight) {
+    while (true) {
+        unsigned idle = __ballot_sync(0xffffffffu, slot < 0);
+        if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+            long long got = warp_pool_take<B2PT_WF_CHUNK>(pool, &W.totals[5], total, slot < 0);
+            if (slot < 0 && got >= 0) {
+                const long long nsh = total / nl;
+                int l = (int)(got / nsh), k = (int)(got - (long long)l * nsh);   // light-major: a warp's rays aim at one light
+                int p = W.q_shadow[k];
+                float4 g0 = W.g0[p], g1 = W.g1[p];
+                V3 P = f4v(g0), n = f4v(g1);
                 const DLight& lt = S.lights[l];
                 V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
                 float dist = vlength(lightDir);
-                if (!(dist < 0.0001f)) {                                          // :263-269
+                slot = (long long)p * nl + l;
+                if (dist < 0.0001f || S.nwide == 0) {       // :263-269 light skipped (shade skips it too) / empty scene
+                    W.vis[slot] = 0;
+                    slot = -1;
+                } else {
                     lightDir = vnormalize(lightDir);
-                    RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));   // :274-275
-                    int occ = any_octet<COUNT>(S, g, r, n_nodes, n_tris);
-                    if (occ < 0) { HitRec h; closest_exact_dfs(S, r, h); occ = h.tri >= 0; }
-                    if (!occ) {
-                        float cosTheta = gmax(vdot(n, lightDir), 0.0f);
-                        float att = B2PT_DIV(lt.intensity, B2PT_MUL(dist, dist));
-                        V3 brdf;
-                        if (m.type == B2PT_DIFFUSE) {
-                            brdf = vdivs(mk3(m.r, m.g, m.b), 3.14159265358979323846264338327950288f);
-                        } else {
-                            V3 halfVec = vnormalize(vadd(lightDir, viewDir));
-                            float NdotH = gmax(vdot(n, halfVec), 0.0f);
-                            brdf = vmuls(mk3(m.r, m.g, m.b), ggx_distribution(NdotH, m.roughness));
-                        }
-                        V3 c = vmuls(vmuls(vmul(mk3(lt.cr, lt.cg, lt.cb), brdf), cosTheta), att);
-                        if (valid3(c)) { cx = c.x; cy = c.y; cz = c.z; addf = 1; }
-                    }
+                    lane_begin(st, make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f)));   // :274-275
                 }
             }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < GPV; ++q) {
-                int src = (vslot * GPV + q) * 8;
-                float ax = __shfl_sync(0xffffffffu, cx, src);
-                float ay = __shfl_sync(0xffffffffu, cy, src);
-                float az = __shfl_sync(0xffffffffu, cz, src);
-                int af = __shfl_sync(0xffffffffu, addf, src);
-                if (af) { tx = B2PT_ADD(tx, ax); ty = B2PT_ADD(ty, ay); tz = B2PT_ADD(tz, az); }
+            if (__ballot_sync(0xffffffffu, slot >= 0) == 0 && pool.exhausted) break;
+        }
+        if (slot >= 0) {
+            int res = lane_any_step<COUNT, TPS>(S, st, n_nodes, n_tris);
+            if (res) {
+                if (res == 3) { HitRec h; closest_exact_dfs(S, st.r, h); res = h.tri >= 0 ? 1 : 2; }
+                W.vis[slot] = res == 1 ? 1 : 0;
+                slot = -1;
             }
         }
-        if (live && lsub == 0 && g.gl == 0) W.direct[p] = make_float4(tx, ty, tz, 0.0f);
     }
     if (COUNT) {
-        __syncwarp();
         for (int off = 16; off > 0; off >>= 1) {
             n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
             n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
         }
-        if (lane == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
     }
+}
+
+// calculateDirectLighting (renderer.hpp:252-301) given the visibility of every light.
+__device__ __forceinline__ V3 direct_lighting(const DeviceScene& S, const DMaterial& m, V3 P, V3 n, V3 viewDir, const uint8_t* __restrict__ vis) {
+    V3 total = mk3(0.0f, 0.0f, 0.0f);
+    for (int l = 0; l < S.nlight; ++l) {
+        const DLight& lt = S.lights[l];
+        V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
+        float dist = vlength(lightDir);
+        if (dist < 0.0001f) continue;                                     // :263-269
+        if (vis[l]) continue;                                             // :278
+        lightDir = vnormalize(lightDir);
+        float cosTheta = gmax(vdot(n, lightDir), 0.0f);
+        float att = B2PT_DIV(lt.intensity, B2PT_MUL(dist, dist));
+        V3 brdf;
+        if (m.type == B2PT_DIFFUSE) {
+            brdf = vdivs(mk3(m.r, m.g, m.b), 3.14159265358979323846264338327950288f);
+        } else {
+            V3 halfVec = vnormalize(vadd(lightDir, viewDir));
+            float NdotH = gmax(vdot(n, halfVec), 0.0f);
+            brdf = vmuls(mk3(m.r, m.g, m.b), ggx_distribution(NdotH, m.roughness));
+        }
+        V3 c = vmuls(vmuls(vmul(mk3(lt.cr, lt.cg, lt.cb), brdf), cosTheta), att);
+        if (valid3(c)) total = vadd(total, c);                            // :295-297
+    }
+    return total;
 }
 
 // tracePath's material switch (renderer.hpp:166-247), one kernel per material type.
@@ -356,8 +424,7 @@ __global__ void __launch_bounds__(256) k_shade(DeviceScene S, Wave W, FrameConst
                 }
             }
         } else {
-            float4 dl = W.direct[p];
-            V3 direct = f4v(dl);
+            V3 direct = direct_lighting(S, m, P, n, vneg(d), W.vis + (long long)p * S.nlight);
             if (valid3(direct)) {                                          // :161-163
                 V3 dir;
                 if (TYPE == B2PT_DIFFUSE) {
@@ -406,6 +473,7 @@ __global__ void k_begin_bounce(Wave W, int cur_slot, int first, int P, int nligh
     W.counters[cur_slot ^ 1] = 0;
     W.counters[C_MAT0] = 0; W.counters[C_MAT1] = 0; W.counters[C_MAT2] = 0;
     W.counters[C_SHADOW] = 0; W.counters[C_FALLBACK] = 0; W.counters[C_NEXT] = 0;
+    W.totals[4] = 0; W.totals[5] = 0;
 }
 __global__ void k_after_extend(Wave W, int nlight) {
     W.totals[1] += (unsigned long long)W.counters[C_SHADOW] * (unsigned long long)nlight;
@@ -453,19 +521,6 @@ __global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ rgb, 
     c = gmin(gmax(c, 0.0f), 1.0f);
     c = powf(c, inv_gamma);
     out[i] = (uint8_t)(c * 255.0f);
-}
-
-template <bool COUNT>
-void launch_direct(const DeviceScene& S, const Wave& W, int P, int nlight, int sm_count, cudaStream_t st, TraceCounters* tc) {
-    int gpv = nlight >= 4 ? 4 : (nlight >= 2 ? 2 : 1);
-    long long warps = ((long long)P * gpv + 3) / 4;
-    unsigned grid = (unsigned)std::min<long long>((warps + 3) / 4, (long long)sm_count * 16);
-    if (grid == 0) grid = 1;
-    switch (gpv) {
-        case 1: k_direct<1, COUNT><<<grid, B2PT_WF_BLOCK, 0, st>>>(S, W, tc); break;
-        case 2: k_direct<2, COUNT><<<grid, B2PT_WF_BLOCK, 0, st>>>(S, W, tc); break;
-        default: k_direct<4, COUNT><<<grid, B2PT_WF_BLOCK, 0, st>>>(S, W, tc); break;
-    }
 }
 
 }  // namespace
@@ -529,16 +584,18 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     // scratch: slot 8 = path state + queues, slot 9 = accumulators, slot 10 = counters/totals
     size_t f4 = sizeof(float4) * (size_t)Pmax, qi = sizeof(int) * (size_t)Pmax;
     void* base = nullptr;
-    int rc = scratch_reserve(ctx, 8, 8 * f4 + 7 * qi + 1024, &base);
+    size_t vb = ((size_t)Pmax * (size_t)std::max(S.nlight, 1) + 255) & ~(size_t)255;
+    int rc = scratch_reserve(ctx, 8, 7 * f4 + 7 * qi + vb + 1024, &base);
     if (rc) return rc;
     Wave Wv{};
     {
         char* b = (char*)base;
         Wv.ro = (float4*)b; b += f4; Wv.rd = (float4*)b; b += f4; Wv.hit = (float4*)b; b += f4; Wv.g0 = (float4*)b; b += f4; Wv.g1 = (float4*)b; b += f4;
-        Wv.direct = (float4*)b; b += f4; Wv.thr = (float4*)b; b += f4; Wv.rad = (float4*)b; b += f4;
+        Wv.thr = (float4*)b; b += f4; Wv.rad = (float4*)b; b += f4;
         Wv.q_active[0] = (int*)b; b += qi; Wv.q_active[1] = (int*)b; b += qi;
         Wv.q_mat[0] = (int*)b; b += qi; Wv.q_mat[1] = (int*)b; b += qi; Wv.q_mat[2] = (int*)b; b += qi;
         Wv.q_shadow = (int*)b; b += qi; Wv.q_fallback = (int*)b; b += qi;
+        Wv.vis = (uint8_t*)b; b += vb;
     }
     void* accum = nullptr;
     if ((rc = scratch_reserve(ctx, 9, sizeof(float4) * (size_t)nown, &accum))) return rc;
@@ -550,6 +607,15 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     B2PT_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(float4) * (size_t)nown, stream));
 
     const bool count = (ctx->flags & B2PT_FLAG_COUNT_FETCHES) != 0;
+    const int tu_refill = std::getenv("B2PT_WF_REFILL") ? std::atoi(std::getenv("B2PT_WF_REFILL")) : 4;
+    const int tu_tps = std::getenv("B2PT_WF_TPS") ? std::atoi(std::getenv("B2PT_WF_TPS")) : 4;
+    // B2PT_WF_MODE: 1 = run-to-completion kernels for every bounce (default), 2 = persistent kernels for every
+    // bounce, 0 = run-to-completion for depth 0 and small scenes, persistent otherwise.  Measured (profiles/
+    // r01_render_modes.txt): queue neighbours are neighbouring pixels, so even bounce rays start from nearby
+    // points and mode 1 wins in every rendered scene tried; the persistent kernels win only on unordered ray
+    // batches (b2pt_trace_*: 2.1 vs 1.0 Grays/s on random rays in 1M triangles).
+    const int force_mode = std::getenv("B2PT_WF_MODE") ? std::atoi(std::getenv("B2PT_WF_MODE")) : 1;
+    const int coherent_nodes = std::getenv("B2PT_COHERENT_NODES") ? std::atoi(std::getenv("B2PT_COHERENT_NODES")) : 512;
     int64_t launches = 0, n_extend = 0, n_shadow = 0;
     float extend_ms = 0.0f, shadow_ms = 0.0f;
     // Traversal time is measured with events around extend+direct of every bounce; to avoid a sync
@@ -570,11 +636,17 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 k_begin_bounce<<<1, 1, 0, stream>>>(Wv, cur, depth == 0, P, S.nlight);
                 const int* list = depth == 0 ? nullptr : Wv.q_active[cur];
                 ev();
-                {
-                    long long octets = ((long long)P + B2PT_WF_BATCH - 1) / B2PT_WF_BATCH;
-                    unsigned egrid = (unsigned)std::min<long long>((octets + B2PT_WF_OCTETS - 1) / B2PT_WF_OCTETS, (long long)ctx->sm_count * 16);
-                    if (count) k_extend<true><<<egrid, B2PT_WF_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    else k_extend<false><<<egrid, B2PT_WF_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                // Coherent batches (camera rays and their shadow rays; any ray of a tiny scene) take the
+                // run-to-completion kernels, incoherent ones the persistent kernels with lane refill.
+                const bool coherent = force_mode == 1 || (force_mode == 0 && (depth == 0 || S.nwide <= coherent_nodes));
+                if (coherent) {
+                    if (count) k_extend_rtc<true><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else k_extend_rtc<false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                } else {
+                    unsigned egrid = (unsigned)std::min<long long>(((long long)P + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (long long)ctx->sm_count * 12);
+                    if (count) k_extend<true, 4><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else if (tu_tps == 8) k_extend<false, 8><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else k_extend<false, 4><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 }
                 k_extend_fallback<<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
                 k_hitinfo<<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
@@ -583,8 +655,16 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 ++n_extend;
                 if (S.nlight > 0) {
                     ++n_shadow;
-                    if (count) launch_direct<true>(S, Wv, P, S.nlight, ctx->sm_count, stream, ctx->d_counters);
-                    else launch_direct<false>(S, Wv, P, S.nlight, ctx->sm_count, stream, ctx->d_counters);
+                    if (coherent) {
+                        unsigned sg = (unsigned)(((long long)P * S.nlight + 127) / 128);
+                        if (count) k_shadow_rtc<true><<<sg, 128, 0, stream>>>(S, Wv, ctx->d_counters);
+                        else k_shadow_rtc<false><<<sg, 128, 0, stream>>>(S, Wv, ctx->d_counters);
+                    } else {
+                        unsigned sgrid = (unsigned)std::min<long long>(((long long)P * S.nlight + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (long long)ctx->sm_count * 12);
+                        if (count) k_shadow<true, 4><<<sgrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, ctx->d_counters);
+                        else if (tu_tps == 8) k_shadow<false, 8><<<sgrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, ctx->d_counters);
+                        else k_shadow<false, 4><<<sgrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, ctx->d_counters);
+                    }
                     ++launches;
                 }
                 ev();

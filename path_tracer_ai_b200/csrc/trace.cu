@@ -6,6 +6,7 @@
 // it cannot certify (bit-equal ties, winner on its own leaf box's entry face) are appended to a
 // fallback list and re-run by k_closest_exact, the flattened reference recursion.
 #include <algorithm>
+#include <cstdlib>
 #include "traverse_thread.cuh"
 
 namespace b2pt {
@@ -121,14 +122,16 @@ __global__ void __launch_bounds__(B2PT_TRACE_BLOCK) k_any_octet(DeviceScene S, c
 #define B2PT_REFILL_MIN 4       // refill as soon as this many lanes are idle
 #define B2PT_TPS 2              // triangles per step
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_closest_thread(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
+template <bool COUNT, int TPS>
+__global__ void __launch_bounds__(B2PT_TBLOCK) k_closest_thread(int refill_min, DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
                                                         const float* __restrict__ tmax, long long n,
                                                         int32_t* __restrict__ tri, float* __restrict__ t, float* __restrict__ uv,
                                                         unsigned long long* __restrict__ next_ray,
                                                         int* __restrict__ fb_count, int* __restrict__ fb_list,
                                                         TraceCounters* __restrict__ counters) {
+    __shared__ uint2 lane_stacks[B2PT_SSTACK * B2PT_TBLOCK];
     LaneState st;
+    st.stack.sm = lane_stacks + threadIdx.x;
     WarpPool pool{0, 0, false};
     long long idx = -1;
     unsigned n_nodes = 0, n_tris = 0;
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(128) k_closest_thread(DeviceScene S, const flo
     }
     while (true) {
         unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
-        if (idle && (__popc(idle) >= B2PT_REFILL_MIN || idle == 0xffffffffu)) {
+        if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
             long long got = warp_pool_take<B2PT_POOL_CHUNK>(pool, next_ray, n, idx < 0);
             if (idx < 0 && got >= 0) {
                 idx = got;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(128) k_closest_thread(DeviceScene S, const flo
             if (__ballot_sync(0xffffffffu, idx >= 0) == 0) break;   // nothing left anywhere
         }
         if (idx >= 0) {
-            if (lane_closest_step<COUNT, B2PT_TPS>(S, st, n_nodes, n_tris)) {
+            if (lane_closest_step<COUNT, TPS>(S, st, n_nodes, n_tris)) {
                 store_hit(st.best, idx, tri, t, uv);
                 if (!lane_certify(S, st)) fb_list[atomicAdd(fb_count, 1)] = (int)idx;
                 idx = -1;
@@ -160,11 +163,13 @@ __global__ void __launch_bounds__(128) k_closest_thread(DeviceScene S, const flo
     if (COUNT) flush_counters(counters, n_nodes, n_tris);
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_any_thread(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
+template <bool COUNT, int TPS>
+__global__ void __launch_bounds__(B2PT_TBLOCK) k_any_thread(int refill_min, DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
                                                     const float* __restrict__ tmax, long long n, uint8_t* __restrict__ occ,
                                                     unsigned long long* __restrict__ next_ray, TraceCounters* __restrict__ counters) {
+    __shared__ uint2 lane_stacks[B2PT_SSTACK * B2PT_TBLOCK];
     LaneState st;
+    st.stack.sm = lane_stacks + threadIdx.x;
     WarpPool pool{0, 0, false};
     long long idx = -1;
     unsigned n_nodes = 0, n_tris = 0;
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(128) k_any_thread(DeviceScene S, const float* 
     }
     while (true) {
         unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
-        if (idle && (__popc(idle) >= B2PT_REFILL_MIN || idle == 0xffffffffu)) {
+        if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
             long long got = warp_pool_take<B2PT_POOL_CHUNK>(pool, next_ray, n, idx < 0);
             if (idx < 0 && got >= 0) {
                 idx = got;
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(128) k_any_thread(DeviceScene S, const float* 
             if (__ballot_sync(0xffffffffu, idx >= 0) == 0) break;
         }
         if (idx >= 0) {
-            int res = lane_any_step<COUNT, B2PT_TPS>(S, st, n_nodes, n_tris);
+            int res = lane_any_step<COUNT, TPS>(S, st, n_nodes, n_tris);
             if (res) {
                 if (res == 3) { HitRec h; closest_exact_dfs(S, st.r, h); res = h.tri >= 0 ? 1 : 2; }
                 occ[idx] = res == 1 ? 1 : 0;
@@ -192,6 +197,17 @@ __global__ void __launch_bounds__(128) k_any_thread(DeviceScene S, const float* 
         }
     }
     if (COUNT) flush_counters(counters, n_nodes, n_tris);
+}
+
+// Experiment knobs (environment, read once): B2PT_TPS triangles per step {1,2,4,8}, B2PT_REFILL idle lanes that
+// trigger a refill, B2PT_BLOCKS_PER_SM persistent blocks per SM.
+struct Tune { int tps, refill, blocks_per_sm; };
+const Tune& tune() {
+    static const Tune t = [] {
+        auto env = [](const char* k, int dflt) { const char* v = std::getenv(k); return v ? std::atoi(v) : dflt; };
+        return Tune{env("B2PT_TPS", 4), env("B2PT_REFILL", 4), env("B2PT_BLOCKS_PER_SM", 12)};
+    }();
+    return t;
 }
 
 }  // namespace
@@ -226,11 +242,15 @@ int launch_trace_closest(b2pt_ctx* ctx, const float* d_o, const float* d_d, cons
                 else
                     k_closest_octet<false><<<grid, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
             } else {
-                unsigned tgrid = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * 12);
-                if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
-                    k_closest_thread<true><<<tgrid, 128, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
-                else
-                    k_closest_thread<false><<<tgrid, 128, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
+                const Tune tu = tune();
+                unsigned tgrid = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * tu.blocks_per_sm);
+#define LAUNCH_CT(C, T) k_closest_thread<C, T><<<tgrid, 128, 0, st>>>(tu.refill, ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters)
+                if (ctx->flags & B2PT_FLAG_COUNT_FETCHES) LAUNCH_CT(true, 2);
+                else if (tu.tps == 1) LAUNCH_CT(false, 1);
+                else if (tu.tps == 4) LAUNCH_CT(false, 4);
+                else if (tu.tps == 8) LAUNCH_CT(false, 8);
+                else LAUNCH_CT(false, 2);
+#undef LAUNCH_CT
             }
             k_closest_exact<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, ctx->d_fallback_count, (const int*)fb, ctx->d_counters);
             ctx->stats.kernel_launches += 2;
@@ -257,11 +277,15 @@ int launch_trace_any(b2pt_ctx* ctx, const float* d_o, const float* d_d, const fl
             else
                 k_any_octet<false><<<grid, B, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
         } else {
-            unsigned tgrid = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * 12);
-            if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
-                k_any_thread<true><<<tgrid, 128, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
-            else
-                k_any_thread<false><<<tgrid, 128, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
+            const Tune tu = tune();
+            unsigned tgrid = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * tu.blocks_per_sm);
+#define LAUNCH_AT(C, T) k_any_thread<C, T><<<tgrid, 128, 0, ctx->stream>>>(tu.refill, ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters)
+            if (ctx->flags & B2PT_FLAG_COUNT_FETCHES) LAUNCH_AT(true, 2);
+            else if (tu.tps == 1) LAUNCH_AT(false, 1);
+            else if (tu.tps == 4) LAUNCH_AT(false, 4);
+            else if (tu.tps == 8) LAUNCH_AT(false, 8);
+            else LAUNCH_AT(false, 2);
+#undef LAUNCH_AT
         }
         ctx->stats.kernel_launches += 1;
         B2PT_CUDA(ctx, cudaGetLastError());

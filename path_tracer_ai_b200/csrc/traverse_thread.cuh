@@ -15,6 +15,21 @@
 namespace b2pt {
 
 #define B2PT_TSTACK 64   // 7 pushes per wide level, <= 9 levels below 2^28 triangles
+#define B2PT_SSTACK 16   // entries of each lane's stack that live in shared memory (the rest: local memory)
+#define B2PT_TBLOCK 128  // block size of the per-lane kernels (stride of the shared stack layout)
+
+// Per-lane stack: the first B2PT_SSTACK entries are in shared memory, laid out entry-major
+// (entry e of thread t at smem[e * B2PT_TBLOCK + t]): the 8-byte accesses of a warp hit distinct banks
+// whatever depth each lane is at.  ncu on the all-local version: 4.2 KB of local-memory traffic per ray,
+// long-scoreboard the top stall, L1 at 76 % (profiles/r01_ncu_closest_v3_persistent.txt).  Deeper
+// entries (rare) overflow into a small local array.
+struct LaneStack {
+    uint2* sm;                                    // &smem[threadIdx.x]
+    uint2 ovf[B2PT_TSTACK - B2PT_SSTACK];
+    __device__ __forceinline__ uint2 get(int i) const { return i < B2PT_SSTACK ? sm[i * B2PT_TBLOCK] : ovf[i - B2PT_SSTACK]; }
+    __device__ __forceinline__ void set(int i, uint2 v) { if (i < B2PT_SSTACK) sm[i * B2PT_TBLOCK] = v; else ovf[i - B2PT_SSTACK] = v; }
+};
+#define B2PT_LANE_SMEM_BYTES (B2PT_SSTACK * B2PT_TBLOCK * 8)
 
 struct LaneState {
     RayQ r;
@@ -25,7 +40,7 @@ struct LaneState {
     int tri_next, tri_end; // triangles of the current leaf still to test
     bool tie;
     bool overflow;
-    uint2 stack[B2PT_TSTACK];   // (child code, entry distance bits)
+    LaneStack stack;       // (child code, entry distance bits)
 };
 
 __device__ __forceinline__ void lane_begin(LaneState& st, const RayQ& r) {
@@ -65,11 +80,16 @@ __device__ __forceinline__ void lane_node_step(const DeviceScene& S, LaneState& 
             slab_axis(ly[s], hy[s], st.r.o.y, st.r.invD.y, tmin, tmax);
             slab_axis(lz[s], hz[s], st.r.o.z, st.r.invD.z, tmin, tmax);
             if (ANY) {
-                if (tmax > tmin) st.stack[sp++] = make_uint2(cd[s], 0u);
+                if (tmax > tmin) st.stack.set(sp++, make_uint2(cd[s], 0u));
             } else if (tmax > tmin && tmin <= st.cull) {
                 int j = sp++;
-                while (j > base && __uint_as_float(st.stack[j - 1].y) < tmin) { st.stack[j] = st.stack[j - 1]; --j; }
-                st.stack[j] = make_uint2(cd[s], __float_as_uint(tmin));
+                while (j > base) {
+                    uint2 prev = st.stack.get(j - 1);
+                    if (!(__uint_as_float(prev.y) < tmin)) break;
+                    st.stack.set(j, prev);
+                    --j;
+                }
+                st.stack.set(j, make_uint2(cd[s], __float_as_uint(tmin)));
             }
         }
     }
@@ -80,7 +100,7 @@ __device__ __forceinline__ void lane_node_step(const DeviceScene& S, LaneState& 
 template <bool ANY>
 __device__ __forceinline__ bool lane_pop(LaneState& st) {
     while (st.sp > 0) {
-        uint2 e = st.stack[--st.sp];
+        uint2 e = st.stack.get(--st.sp);
         if (ANY || __uint_as_float(e.y) <= st.cull) {
             if (e.x & B2PT_CHILD_LEAF) {
                 st.tri_next = e.x & 0x0FFFFFFF;

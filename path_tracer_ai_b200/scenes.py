@@ -188,7 +188,7 @@ def _noise(u, v, rng, octaves=4):
     return out
 
 
-def mesh_scene(ntri: int = 1_000_000, seed: int = 1234, dielectric_fraction: float = 0.15):
+def mesh_scene(ntri: int = 1_000_000, seed: int = 1234, dielectric_fraction: float = 0.15, room: bool = True):
     """Returns dict(pos[n,9], nrm[n,9], mat[n], materials8[m,8], lo, hi) in world space (pre-build order).
 
     ~32 % of the triangles form a displaced terrain, the rest 8 displaced tori / spheres.  Material mix by
@@ -255,11 +255,25 @@ def mesh_scene(ntri: int = 1_000_000, seed: int = 1234, dielectric_fraction: flo
         if np.mean(np.sum(fn * outward, 1)) < 0:
             nrm = -nrm
         parts.append((pos, nrm, obj_mats[k]))
+    if room:
+        # the 8 room triangles Scene::loadFromObj always adds (reference src/scene.cpp:118-209): floor 16x16 at
+        # y=0, back / left / right walls of height 4, diffuse 0.9; first in the pre-build order, as there
+        R, Hh = 8.0, 4.0
+        quads = [((-R, 0, -R), (R, 0, -R), (R, 0, R), (-R, 0, R), (0, 1, 0)),
+                 ((-R, 0, -R), (-R, Hh, -R), (R, Hh, -R), (R, 0, -R), (0, 0, 1)),
+                 ((-R, 0, -R), (-R, 0, R), (-R, Hh, R), (-R, Hh, -R), (1, 0, 0)),
+                 ((R, 0, -R), (R, Hh, -R), (R, Hh, R), (R, 0, R), (-1, 0, 0))]
+        rp, rn = [], []
+        for a, b, c, d, n in quads:
+            rp += [a + b + c, a + c + d]
+            rn += [n * 3, n * 3]
+        materials.append((DIFFUSE, (0.9, 0.9, 0.9), 0.95, 0.0, 1.5))
+        parts.insert(0, (np.array(rp, np.float64), np.array(rn, np.float64), len(materials) - 1))
     pos = np.concatenate([p for p, _, _ in parts]).astype(np.float32)
     nrm = np.concatenate([n for _, n, _ in parts]).astype(np.float32)
     mat = np.concatenate([np.full(len(p), mid, np.int32) for p, _, mid in parts])
     m8 = np.zeros((len(materials), 8), np.float32)
     for i, (ty, alb, rough, metal, ior) in enumerate(materials):
         m8[i] = (ty, alb[0], alb[1], alb[2], rough, metal, ior, 0.0)
-    V = pos.reshape(-1, 3)
+    V = pos[8:].reshape(-1, 3) if room else pos.reshape(-1, 3)   # lo/hi: the mesh itself (ray generators), not the 16-unit room
     return dict(pos=pos, nrm=nrm, mat=mat, materials8=m8, lo=V.min(0), hi=V.max(0))

@@ -27,7 +27,7 @@ if args.soup:
     pos = scenes.random_soup(args.tris, 1234, size=2.0 / np.cbrt(args.tris))
     ms = dict(pos=pos, nrm=None, mat=None, materials8=None, lo=pos.reshape(-1, 3).min(0), hi=pos.reshape(-1, 3).max(0))
 else:
-    ms = scenes.mesh_scene(args.tris, seed=1234)
+    ms = scenes.mesh_scene(args.tris, seed=1234, room=False)
 t1 = time.time()
 order = pt.reference_order(ms["pos"])
 t2 = time.time()
