@@ -183,6 +183,7 @@ def main():
     import torch.distributed as dist
 
     import path_tracer_ai_b200 as pt
+    from path_tracer_ai_b200 import distributed as D
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU arm)")
@@ -201,11 +202,11 @@ def main():
 
     if args.scaling == "weak":
         spp_total = SPP * world
-        part = None if world == 1 else dict(sample_begin=SPP * rank, sample_count=SPP)
+        part = D.sample_partition(rank, world, SPP)
         parallelism = f"sample ranges x{world}, scene replicated, 1 NCCL reduce/frame" if world > 1 else "single GPU"
     else:
         spp_total = SPP
-        part = None if world == 1 else dict(tile_rank=rank, tile_world=world, tile_size=32)
+        part = D.tile_partition(rank, world, 32)
         parallelism = f"interleaved 1024-pixel tiles x{world}, scene replicated, 1 NCCL reduce/frame" if world > 1 else "single GPU"
 
     d_rgb = torch.empty(W * H * 3, dtype=torch.float32, device=dev)
@@ -214,11 +215,8 @@ def main():
     def step_device():
         flush.zero_()                      # L2 flush between iterations (on torch's stream; synchronised below)
         torch.cuda.synchronize(dev)
-        eng.render_device(cam.c, W, H, spp_total, B, d_rgb.data_ptr(), seed=1234, part=part)   # synchronous on the engine's stream
-        st = eng.stats()
-        if world > 1:
-            dist.reduce(d_rgb, dst=0, op=dist.ReduceOp.SUM)
-        return st
+        # render (synchronous on the engine's stream) + the frame's one collective (NCCL sum-reduce to rank 0)
+        return D.render_distributed(eng, cam.c, W, H, spp_total, B, d_rgb, part, seed=1234)
 
     def barrier():
         if world > 1:

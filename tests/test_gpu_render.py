@@ -69,11 +69,14 @@ def test_render_independent_of_chunking_and_partition(built, cornell):
     small = pt.Engine(max_paths=5000)
     small.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
     assert np.array_equal(bits(small.render(cam.c, W, H, SPP, B, seed=4)), bits(ref))
+    from path_tracer_ai_b200 import distributed as D
     for world in (2, 3, 8):
         acc = np.zeros_like(ref)
+        owner = D.owner_map(W, H, world, 8)
         for rank in range(world):
-            part = big.render(cam.c, W, H, SPP, B, seed=4, part=dict(tile_rank=rank, tile_world=world, tile_size=8))
+            part = big.render(cam.c, W, H, SPP, B, seed=4, part=D.tile_partition(rank, world, 8))
             assert np.all((part == 0) | (acc == 0))     # disjoint ownership
+            assert np.all(part[owner != rank] == 0)     # host-side ownership rule == the kernels'
             acc += part
         assert np.array_equal(bits(acc), bits(ref))
     a = big.render(cam.c, W, H, SPP, B, seed=4, part=dict(sample_begin=0, sample_count=2))
