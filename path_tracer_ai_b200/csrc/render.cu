@@ -64,18 +64,6 @@ __device__ __forceinline__ long long pixel_of(const FrameConst& F, long long j) 
     return j;
 }
 
-// Warp-aggregated queue append; must be reached by all 32 lanes of the warp.
-__device__ __forceinline__ void warp_append(int* counter, int* queue, bool pred, int value) {
-    unsigned mask = __ballot_sync(0xffffffffu, pred);
-    if (mask == 0) return;
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(mask) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
-}
-
 __device__ __forceinline__ V3 f4v(float4 a) { return mk3(a.x, a.y, a.z); }
 
 // renderer.hpp:308-319: rejection-sample the cube, NORMALISE the accepted point.
@@ -108,10 +96,10 @@ __global__ void __launch_bounds__(256) k_raygen(Wave W, CamConst C, FrameConst F
 
 // After a closest hit: hit point, shading normal (normalised three times: triangle.hpp:62,
 // intersection.hpp:18, renderer.hpp:139), material lookup (renderer.hpp:141-148), binning.
-struct Epilogue { bool m0, m1, m2, shadow; };
+struct Epilogue { bool m0, m1, m2; unsigned lights; };   // lights: bit l = vertex needs a shadow ray towards light l
 
 __device__ __forceinline__ Epilogue hit_epilogue(const DeviceScene& S, const Wave& W, int p, V3 o, V3 d, const HitRec& h) {
-    Epilogue e{false, false, false, false};
+    Epilogue e{false, false, false, 0u};
     if (h.tri < 0) return e;   // miss: black background, path ends (renderer.hpp:135-137)
     float4 a = __ldg(&S.nrm[3ll * h.tri + 0]), b = __ldg(&S.nrm[3ll * h.tri + 1]), c = __ldg(&S.nrm[3ll * h.tri + 2]);
     float w = B2PT_SUB(B2PT_SUB(1.0f, h.u), h.v);
@@ -130,15 +118,95 @@ __device__ __forceinline__ Epilogue hit_epilogue(const DeviceScene& S, const Wav
     W.g0[p] = make_float4(P.x, P.y, P.z, __int_as_float(mat));
     W.g1[p] = make_float4(n.x, n.y, n.z, 0.0f);
     e.m0 = type == B2PT_DIFFUSE; e.m1 = type == B2PT_SPECULAR; e.m2 = type == B2PT_DIELECTRIC;
-    e.shadow = e.m0 || e.m1;
+    if (e.m0 || e.m1) {
+        // calculateDirectLighting (renderer.hpp:258-299) traces a shadow ray towards every light and only then
+        // multiplies by cosTheta = max(dot(n, l), 0).  A light at or below the horizon (dot <= 0) therefore
+        // contributes exactly zero whatever the ray finds — +-0 added to the sum, or a NaN the validity check
+        // drops (:295) — and so does a light closer than 1e-4 (:263).  Those rays are not traced: the light is
+        // marked "nothing to add" in vis and the image is bit-identical.  Same n, same normalised lightDir, same
+        // dot as direct_lighting() computes later, so the two decisions cannot disagree.
+        uint8_t* vis = W.vis + (long long)p * S.nlight;
+        for (int l = 0; l < S.nlight; ++l) {
+            const DLight& lt = S.lights[l];
+            V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
+            float dist = vlength(lightDir);
+            bool trace = false;
+            if (!(dist < 0.0001f)) trace = !(vdot(n, vnormalize(lightDir)) <= 0.0f);
+            if (trace) e.lights |= 1u << l; else vis[l] = 1;
+        }
+    }
     return e;
 }
 
-__device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p) {
-    warp_append(&W.counters[C_MAT0], W.q_mat[0], e.m0, p);
-    warp_append(&W.counters[C_MAT1], W.q_mat[1], e.m1, p);
-    warp_append(&W.counters[C_MAT2], W.q_mat[2], e.m2, p);
-    warp_append(&W.counters[C_SHADOW], W.q_shadow, e.shadow, p);
+// Block-aggregated queue appends (256-thread blocks, every thread must call).  One atomic per block and
+// destination instead of one per warp: the per-warp version issued ~1M atomics per launch on a single
+// address, and same-address atomics retire at roughly one per L2 clock — that alone was ~1 ms per launch.
+#define B2PT_BIN_BLOCK 256
+#define B2PT_BIN_WARPS (B2PT_BIN_BLOCK / 32)
+
+__device__ __forceinline__ void block_append(int* counter, int* queue, bool pred, int value) {
+    __shared__ int s_w[B2PT_BIN_WARPS];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned b = __ballot_sync(0xffffffffu, pred);
+    if (lane == 0) s_w[w] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < B2PT_BIN_WARPS; ++i) { int t = s_w[i]; s_w[i] = tot; tot += t; }
+        s_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    if (pred) queue[s_base + s_w[w] + __popc(b & ((1u << lane) - 1u))] = value;
+}
+
+// The one-pass counting sort after a closest hit: the path goes into the queue of its material type, and one
+// entry p*nlight + l per needed shadow ray goes into the shadow queue.  Shadow entries of a block are written
+// light-major — (light, warp, lane) — so consecutive entries are neighbouring vertices aiming at the same
+// light (coherent warps in the shadow kernels), and the runs of one vertex group sit next to each other (their
+// g0/g1 are fetched from DRAM once).
+__device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p, int nlight) {
+    constexpr int MAXROWS = 3 + B2PT_MAX_LIGHTS;
+    __shared__ int s_cnt[MAXROWS * B2PT_BIN_WARPS + 1];
+    __shared__ int s_base[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nrows = 3 + nlight, n = nrows * B2PT_BIN_WARPS;
+    const unsigned rowbits = (e.m0 ? 1u : 0u) | (e.m1 ? 2u : 0u) | (e.m2 ? 4u : 0u) | (e.lights << 3);
+    for (int r = 0; r < nrows; ++r) {
+        unsigned b = __ballot_sync(0xffffffffu, (rowbits >> r) & 1u);
+        if (lane == 0) s_cnt[r * B2PT_BIN_WARPS + w] = __popc(b);
+    }
+    __syncthreads();
+    if (w == 0) {
+        // exclusive scan of the n <= 152 counts: 5 consecutive entries per lane + a warp scan
+        int v[5], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { int idx = lane * 5 + k; v[k] = idx < n ? s_cnt[idx] : 0; sum += v[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+        int excl = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { int idx = lane * 5 + k; if (idx < n) s_cnt[idx] = excl; excl += v[k]; }
+        if (lane == 31) s_cnt[n] = incl;
+        __syncwarp();
+        if (lane < 4) {
+            int start = s_cnt[min(lane * B2PT_BIN_WARPS, n)];
+            int end = lane < 3 ? s_cnt[min((lane + 1) * B2PT_BIN_WARPS, n)] : s_cnt[n];
+            int cnt = end - start;
+            int base = cnt ? atomicAdd(&W.counters[lane < 3 ? C_MAT0 + lane : C_SHADOW], cnt) : 0;
+            s_base[lane] = base - start;
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < nrows; ++r) {
+        unsigned b = __ballot_sync(0xffffffffu, (rowbits >> r) & 1u);
+        if ((rowbits >> r) & 1u) {
+            int at = s_base[min(r, 3)] + s_cnt[r * B2PT_BIN_WARPS + w] + __popc(b & ((1u << lane) - 1u));
+            if (r < 3) W.q_mat[r][at] = p; else W.q_shadow[at] = p * nlight + (r - 3);
+        }
+    }
 }
 
 #define B2PT_WF_CHUNK 256   // queue entries a warp claims per global atomic
@@ -220,25 +288,20 @@ __global__ void __launch_bounds__(128) k_extend_rtc(DeviceScene S, Wave W, const
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_shadow_rtc(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
     const int nl = S.nlight;
-    const long long nsh = W.counters[C_SHADOW];
-    const long long total = nsh * nl;
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = W.counters[C_SHADOW];
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned n_nodes = 0, n_tris = 0;
     if (j < total) {
-        int l = (int)(j / nsh), k = (int)(j - (long long)l * nsh);   // light-major
-        int p = W.q_shadow[k];
+        int e = W.q_shadow[j];
+        int p = e / nl, l = e - p * nl;
         float4 g0 = W.g0[p], g1 = W.g1[p];
         V3 P = f4v(g0), n = f4v(g1);
         const DLight& lt = S.lights[l];
         V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
         float dist = vlength(lightDir);
-        uint8_t occ = 0;
-        if (!(dist < 0.0001f)) {
-            lightDir = vnormalize(lightDir);
-            RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));
-            occ = any_rtc<COUNT>(S, r, n_nodes, n_tris) ? 1 : 0;
-        }
-        W.vis[(long long)p * nl + l] = occ;
+        lightDir = vnormalize(lightDir);
+        RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));   // renderer.hpp:271-275
+        W.vis[e] = any_rtc<COUNT>(S, r, n_nodes, n_tris) ? 1 : 0;
     }
     if (COUNT) {
         for (int off = 16; off > 0; off >>= 1) {
@@ -266,10 +329,10 @@ __global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) 
 }
 
 // Hit record -> hit point / shading normal / material, and the one-pass counting sort by material type.
-__global__ void __launch_bounds__(256) k_hitinfo(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr, int P) {
+__global__ void __launch_bounds__(B2PT_BIN_BLOCK) k_hitinfo(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr, int P) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int total = list ? *count_ptr : P;
-    Epilogue e{false, false, false, false};
+    Epilogue e{false, false, false, 0u};
     int p = 0;
     if (k < total) {
         p = list ? list[k] : k;
@@ -278,7 +341,7 @@ __global__ void __launch_bounds__(256) k_hitinfo(DeviceScene S, Wave W, const in
         h.t = h4.x; h.tri = __float_as_int(h4.y); h.u = h4.z; h.v = h4.w;
         e = hit_epilogue(S, W, p, f4v(o4), f4v(d4), h);
     }
-    bin_path(W, e, p);
+    bin_path(W, e, p, S.nlight);
 }
 
 // material.hpp:28-42
@@ -309,7 +372,7 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_shadow(int refill_min, DeviceSc
     st.stack.sm = lane_stacks + threadIdx.x;
     WarpPool pool{0, 0, false};
     const int nl = S.nlight;
-    const long long total = (long long)W.counters[C_SHADOW] * nl;
+    const long long total = W.counters[C_SHADOW];
     long long slot = -1;   // index into vis of the ray this lane is tracing
     unsigned n_nodes = 0, n_tris = 0;
     while (true) {
@@ -317,16 +380,15 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_shadow(int refill_min, DeviceSc
         if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
             long long got = warp_pool_take<B2PT_WF_CHUNK>(pool, &W.totals[5], total, slot < 0);
             if (slot < 0 && got >= 0) {
-                const long long nsh = total / nl;
-                int l = (int)(got / nsh), k = (int)(got - (long long)l * nsh);   // light-major: a warp's rays aim at one light
-                int p = W.q_shadow[k];
+                int e = W.q_shadow[got];
+                int p = e / nl, l = e - p * nl;
                 float4 g0 = W.g0[p], g1 = W.g1[p];
                 V3 P = f4v(g0), n = f4v(g1);
                 const DLight& lt = S.lights[l];
                 V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
                 float dist = vlength(lightDir);
-                slot = (long long)p * nl + l;
-                if (dist < 0.0001f || S.nwide == 0) {       // :263-269 light skipped (shade skips it too) / empty scene
+                slot = e;
+                if (S.nwide == 0) {       // empty scene
                     W.vis[slot] = 0;
                     slot = -1;
                 } else {
@@ -380,16 +442,13 @@ __device__ __forceinline__ V3 direct_lighting(const DeviceScene& S, const DMater
     return total;
 }
 
-// tracePath's material switch (renderer.hpp:166-247), one kernel per material type.
+// tracePath's material switch (renderer.hpp:166-247) for one vertex of material type TYPE; returns whether the
+// path continues (its next ray is then in ro/rd).
 template <int TYPE>
-__global__ void __launch_bounds__(256) k_shade(DeviceScene S, Wave W, FrameConst F, long long pix_begin, int npc, int s_begin,
-                                               int depth, int next_slot) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = W.counters[C_MAT0 + TYPE];
+__device__ __forceinline__ bool shade_vertex(const DeviceScene& S, const Wave& W, const FrameConst& F, long long pix_begin, int npc, int s_begin,
+                                             int depth, int p) {
     bool cont = false;
-    int p = 0;
-    if (k < total) {
-        p = W.q_mat[TYPE][k];
+    {
         float4 g0 = W.g0[p], g1 = W.g1[p], d4 = W.rd[p];
         V3 P = f4v(g0), n = f4v(g1), d = f4v(d4);
         const DMaterial m = S.mats[__float_as_int(g0.w)];
@@ -462,7 +521,29 @@ __global__ void __launch_bounds__(256) k_shade(DeviceScene S, Wave W, FrameConst
             }
         }
     }
-    warp_append(&W.counters[next_slot], W.q_active[next_slot], cont, p);
+    return cont;
+}
+
+// One launch shades all three material queues: thread k takes entry k of the concatenation diffuse | specular |
+// dielectric, so a block is branch-free on the material except where two queues meet.
+__global__ void __launch_bounds__(B2PT_BIN_BLOCK) k_shade(DeviceScene S, Wave W, FrameConst F, long long pix_begin, int npc, int s_begin,
+                                                           int depth, int next_slot) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c0 = W.counters[C_MAT0], c1 = W.counters[C_MAT1], c2 = W.counters[C_MAT2];
+    if (blockIdx.x * blockDim.x >= c0 + c1 + c2) return;   // whole block beyond the queues (uniform)
+    bool cont = false;
+    int p = 0;
+    if (k < c0) {
+        p = W.q_mat[0][k];
+        cont = shade_vertex<B2PT_DIFFUSE>(S, W, F, pix_begin, npc, s_begin, depth, p);
+    } else if (k < c0 + c1) {
+        p = W.q_mat[1][k - c0];
+        cont = shade_vertex<B2PT_SPECULAR>(S, W, F, pix_begin, npc, s_begin, depth, p);
+    } else if (k < c0 + c1 + c2) {
+        p = W.q_mat[2][k - c0 - c1];
+        cont = shade_vertex<B2PT_DIELECTRIC>(S, W, F, pix_begin, npc, s_begin, depth, p);
+    }
+    block_append(&W.counters[next_slot], W.q_active[next_slot], cont, p);
 }
 
 // Bookkeeping between bounces (single thread): totals, reset the per-bounce counters.
@@ -476,7 +557,7 @@ __global__ void k_begin_bounce(Wave W, int cur_slot, int first, int P, int nligh
     W.totals[4] = 0; W.totals[5] = 0;
 }
 __global__ void k_after_extend(Wave W, int nlight) {
-    W.totals[1] += (unsigned long long)W.counters[C_SHADOW] * (unsigned long long)nlight;
+    W.totals[1] += (unsigned long long)W.counters[C_SHADOW];
     W.totals[2] += (unsigned long long)W.counters[C_FALLBACK];
 }
 
@@ -577,6 +658,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
 
     // chunking
     long long maxp = std::max<long long>(ctx->max_paths, 1024);
+    maxp = std::min<long long>(maxp, 0x7fffffffll / std::max(S.nlight, 1));   // shadow-queue entries p*nlight + l are ints
     int npc_max = (int)std::min<long long>(nown, maxp);
     int ns_max = (int)std::max<long long>(1, std::min<long long>(s_count, maxp / npc_max));
     long long Pmax = (long long)npc_max * ns_max;
@@ -585,7 +667,8 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     size_t f4 = sizeof(float4) * (size_t)Pmax, qi = sizeof(int) * (size_t)Pmax;
     void* base = nullptr;
     size_t vb = ((size_t)Pmax * (size_t)std::max(S.nlight, 1) + 255) & ~(size_t)255;
-    int rc = scratch_reserve(ctx, 8, 7 * f4 + 7 * qi + vb + 1024, &base);
+    const size_t qs = qi * (size_t)std::max(S.nlight, 1);   // shadow queue: one entry per (vertex, light)
+    int rc = scratch_reserve(ctx, 8, 7 * f4 + 6 * qi + qs + vb + 1024, &base);
     if (rc) return rc;
     Wave Wv{};
     {
@@ -594,7 +677,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
         Wv.thr = (float4*)b; b += f4; Wv.rad = (float4*)b; b += f4;
         Wv.q_active[0] = (int*)b; b += qi; Wv.q_active[1] = (int*)b; b += qi;
         Wv.q_mat[0] = (int*)b; b += qi; Wv.q_mat[1] = (int*)b; b += qi; Wv.q_mat[2] = (int*)b; b += qi;
-        Wv.q_shadow = (int*)b; b += qi; Wv.q_fallback = (int*)b; b += qi;
+        Wv.q_shadow = (int*)b; b += qs; Wv.q_fallback = (int*)b; b += qi;
         Wv.vis = (uint8_t*)b; b += vb;
     }
     void* accum = nullptr;
@@ -649,7 +732,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                     else k_extend<false, 4><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 }
                 k_extend_fallback<<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
-                k_hitinfo<<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
+                k_hitinfo<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
                 k_after_extend<<<1, 1, 0, stream>>>(Wv, S.nlight);
                 ev();
                 ++n_extend;
@@ -669,10 +752,8 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 }
                 ev();
                 int nxt = cur ^ 1;
-                k_shade<B2PT_DIFFUSE><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
-                k_shade<B2PT_SPECULAR><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
-                k_shade<B2PT_DIELECTRIC><<<(P + 255) / 256, 256, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
-                launches += 8;
+                k_shade<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
+                launches += 6;
             }
             k_resolve<<<(npc + 255) / 256, 256, 0, stream>>>(Wv, (float4*)accum, pix_begin, npc, ns);
             ++launches;
