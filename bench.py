@@ -36,7 +36,9 @@ WORKLOADS = {
     "c1": (800, 450, 10, 5, "BASELINE configs[0]: Cornell box 800x450 10 spp 5 bounces"),
     "c2": (1920, 1080, 100, 5, "BASELINE configs[1]: Cornell box 1920x1080 100 spp 5 bounces"),
     "c3": (1920, 1080, 256, 8, "BASELINE configs[2]: 1M-triangle mesh scene 1920x1080 256 spp 8 bounces"),
+    "c5": (3840, 2160, 1024, 8, "BASELINE configs[4]: 10M-triangle dielectric-heavy scene 3840x2160 1024 spp 8 bounces"),
 }
+# (configs[3], the closest-hit microbench, is tools/bench_trace.py.)
 
 
 def load_peaks():
@@ -93,8 +95,11 @@ def make_scene(workload: str):
     if workload in ("c1", "c2"):
         with tempfile.TemporaryDirectory() as tmp:
             assert sc.loadFromObj(scenes.write_cornell_obj(tmp, seed=1234))
-    else:
+    elif workload == "c3":
         ms = scenes.mesh_scene(1_000_000, seed=1234)
+        sc.setContents(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
+    else:
+        ms = scenes.mesh_scene(10_000_000, seed=1234, dielectric_fraction=0.6)
         sc.setContents(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
     return sc
 
@@ -128,7 +133,7 @@ def reference_arm(args, rank, world):
     # same for every sample index); for the 1M-triangle scene a centre crop as well.
     window = None
     spp = 2 if args.workload != "c1" else SPP
-    if args.workload == "c3":
+    if args.workload in ("c3", "c5"):
         window = (W // 2 - 120, H // 2 - 68, W // 2 + 120, H // 2 + 68)
         spp = 1
     secs0, ns0, kind, cores, _ = cpu_render(sc, W, H, 1, B, args.workload, window)   # calibration (also warms caches)
@@ -298,26 +303,40 @@ def main():
     nrays_c = cst["extend_rays"] + cst["shadow_rays"]
     nodes_per_ray = cst["node_fetches"] / max(nrays_c, 1)
     tris_per_ray = cst["tri_fetches"] / max(nrays_c, 1)
-    dominant = "k_direct (shadow / any-hit)" if agg["shadow_seconds"] >= agg["extend_seconds"] else "k_extend (closest hit)"
-    if agg["shadow_seconds"] >= agg["extend_seconds"]:
-        k_rays, k_secs, k_launches, io = agg["shadow_rays"], agg["shadow_seconds"], agg["shadow_launches"], 48 / 4 + 4
+    shadow_dominant = agg["shadow_seconds"] >= agg["extend_seconds"]
+    dominant = "k_shadow_rtc" if shadow_dominant else "k_extend_rtc"
+    if shadow_dominant:
+        # per shadow ray: read the queue entry (4 B) and the vertex it shares with the other lights
+        # (g0+g1 = 32 B / nlight), write the visibility byte
+        k_rays, k_secs, k_launches, io = agg["shadow_rays"], agg["shadow_seconds"], agg["shadow_launches"], 4 + 32 / max(len(sc.lights), 1) + 1
     else:
-        k_rays, k_secs, k_launches, io = agg["extend_rays"], agg["extend_seconds"], agg["extend_launches"], 32 + 32
+        # per extend ray: read origin + direction (32 B), write the hit record (16 B)
+        k_rays, k_secs, k_launches, io = agg["extend_rays"], agg["extend_seconds"], agg["extend_launches"], 32 + 16
     bytes_per_ray = io + nodes_per_ray * info["wide_node_bytes"] + tris_per_ray * info["tri_bytes"]
     achieved = k_rays * bytes_per_ray / max(k_secs, 1e-12) * 1e-9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get(args.workload, {}).get(dominant)
+        if tj:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": k_rays * bytes_per_ray / max(k_launches, 1),
+                "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "tris_per_ray": tris_per_ray, "kernel_ms_per_launch": 1e3 * k_secs / max(k_launches, 1), "kernel_launches": k_launches,
                 "kernel_share_of_step": k_secs / max(dev_s, 1e-12),
-                "note": "algorithmic bytes = per-ray I/O + mean wide-node fetches x 224 B + mean triangle fetches x 48 B (counting build, "
-                        "1/16-size frame); the 50-triangle scene is L1/L2 resident, so DRAM traffic is far below this"}
+                "note": "algorithmic bytes (SURVEY 8d) = per-ray queue I/O + mean wide-node fetches x 224 B + mean triangle fetches x 48 B, "
+                        "fetch counts from the counting build of the same kernels on a 1/16-size frame. frac > 1 means the node/triangle "
+                        "fetches are served by L1/L2, not HBM (the whole BVH of this workload is cache resident; compare `traffic`, the "
+                        "DRAM bytes ncu measured per launch): the kernel is then bound by instruction issue, not by the memory roofline "
+                        "(ncu: profiles/r01_ncu_c2_batch_v6.txt, issue slots 83 % busy)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         secs0, ns0, kind, cores, _ = cpu_render(sc, W, H, 1, B, args.workload,
-                                                (W // 2 - 120, H // 2 - 68, W // 2 + 120, H // 2 + 68) if args.workload == "c3" else None)
+                                                (W // 2 - 120, H // 2 - 68, W // 2 + 120, H // 2 + 68) if args.workload in ("c3", "c5") else None)
         spp_c = max(1, min(SPP, int(15.0 / max(secs0, 1e-3))))
-        window = (W // 2 - 120, H // 2 - 68, W // 2 + 120, H // 2 + 68) if args.workload == "c3" else None
+        window = (W // 2 - 120, H // 2 - 68, W // 2 + 120, H // 2 + 68) if args.workload in ("c3", "c5") else None
         secs, ns, kind, cores, _ = cpu_render(sc, W, H, spp_c, B, args.workload, window)
         cpu_baseline = {"value": ns / secs * 1e-6, "unit": "Msamples/s", "cores": cores, "kind": kind,
                         "sample": f"{W}x{H}" + (f" crop {window}" if window else "") + f", {spp_c} of {SPP} spp, {B} bounces ({ns} samples, {secs:.1f} s)"}

@@ -209,6 +209,9 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
     }
 }
 
+#ifndef B2PT_EXT_MINB
+#define B2PT_EXT_MINB 8
+#endif
 #define B2PT_WF_CHUNK 256   // queue entries a warp claims per global atomic
 #define B2PT_WF_REFILL 4    // idle lanes that trigger a refill
 
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_extend(int refill_min, DeviceSc
 
 // Run-to-completion variants for coherent batches (traverse_rtc.cuh): one thread per queue entry.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend_rtc(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
+__global__ void __launch_bounds__(128, B2PT_EXT_MINB) k_extend_rtc(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
                                                     int P, TraceCounters* __restrict__ tc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int total = list ? *count_ptr : P;
@@ -706,6 +709,17 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     std::vector<cudaEvent_t> evs;
     auto ev = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); evs.push_back(e); };
 
+    // B2PT_DEBUG_SYNC=1: synchronise after every kernel and name the first one that faults (debugging aid).
+    const bool dbg_sync = std::getenv("B2PT_DEBUG_SYNC") != nullptr;
+    std::string dbg_fault;
+    auto dbg = [&](const char* kernel, long long pb, int sb_, int depth_) {
+        if (!dbg_sync || !dbg_fault.empty()) return;
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess)
+            dbg_fault = std::string(kernel) + " (pixel chunk " + std::to_string(pb) + ", sample chunk " + std::to_string(sb_) + ", depth " +
+                        std::to_string(depth_) + "): " + cudaGetErrorString(e);
+    };
     for (long long pix_begin = 0; pix_begin < nown; pix_begin += npc_max) {
         int npc = (int)std::min<long long>(npc_max, nown - pix_begin);
         for (int sb = 0; sb < s_count; sb += ns_max) {
@@ -714,6 +728,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
             int sabs = s_begin + sb;
             k_raygen<<<(P + 255) / 256, 256, 0, stream>>>(Wv, C, F, pix_begin, npc, sabs, P);
             ++launches;
+            dbg("k_raygen", pix_begin, sb, -1);
             for (int depth = 0; depth < st->max_bounces; ++depth) {
                 int cur = depth & 1;
                 k_begin_bounce<<<1, 1, 0, stream>>>(Wv, cur, depth == 0, P, S.nlight);
@@ -731,8 +746,11 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                     else if (tu_tps == 8) k_extend<false, 8><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                     else k_extend<false, 4><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 }
+                dbg("k_extend", pix_begin, sb, depth);
                 k_extend_fallback<<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
+                dbg("k_extend_fallback", pix_begin, sb, depth);
                 k_hitinfo<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
+                dbg("k_hitinfo", pix_begin, sb, depth);
                 k_after_extend<<<1, 1, 0, stream>>>(Wv, S.nlight);
                 ev();
                 ++n_extend;
@@ -751,12 +769,15 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                     ++launches;
                 }
                 ev();
+                dbg("k_shadow", pix_begin, sb, depth);
                 int nxt = cur ^ 1;
                 k_shade<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
                 launches += 6;
+                dbg("k_shade", pix_begin, sb, depth);
             }
             k_resolve<<<(npc + 255) / 256, 256, 0, stream>>>(Wv, (float4*)accum, pix_begin, npc, ns);
             ++launches;
+            dbg("k_resolve", pix_begin, sb, -1);
         }
     }
     k_finalize<<<(unsigned)((nown + 255) / 256), 256, 0, stream>>>((const float4*)accum, F, nown, all_samples, d_rgb);
@@ -771,6 +792,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
         if (cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]) == cudaSuccess) shadow_ms += ms;
     }
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    if (!dbg_fault.empty()) { ctx->err = "render kernel fault: " + dbg_fault; for (cudaEvent_t e : evs) cudaEventDestroy(e); return B2PT_ERR_CUDA; }
     if (le != cudaSuccess) { cuda_fail(ctx, le, "render kernels", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
     if (ce != cudaSuccess) { cuda_fail(ctx, ce, "cudaMemcpyAsync(totals)", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
     if (se != cudaSuccess) { cuda_fail(ctx, se, "cudaStreamSynchronize", __FILE__, __LINE__); return B2PT_ERR_CUDA; }

@@ -32,6 +32,27 @@ __device__ __forceinline__ RayQ make_rayq(V3 o, V3 d_unnormalised, float T0) {
     return r;
 }
 
+// A ray with a non-finite component never hits anything in the reference.
+//  * NaN component: every slab comparison against a NaN is false, so that axis (for a NaN origin: every axis)
+//    constrains nothing (aabb.hpp:18-21) and the DFS walks into leaves; there Triangle::intersect computes
+//    t = NaN — every `<`/`>` rejection is false for a NaN, so it "accepts" (triangle.hpp:34-58) — and
+//    bvh.hpp:88 discards it because `NaN < isect.t` is false.
+//  * infinite origin component: s = o - v0 is infinite, every product in q = cross(s, e1) and dot(e2, q) that
+//    touches it is +-inf or NaN, so t is never finite; t = +inf passes `t > tMax` (tMax = +inf) but fails
+//    `t < isect.t` (= +inf).
+//  * infinite direction (normalising a vector whose squared length underflows): invD = 0, every t0/t1 is 0 or
+//    NaN, the root box ends with tMax = 0 <= tMin.
+// The answer is a miss / "not occluded" — in the first two cases after walking most of the tree.  The kernels
+// return it at once: such a ray would also pass the boxes of EMPTY child slots (lo = +inf, hi = -inf give NaN
+// slabs), which are not valid triangle ranges, and would hold its warp for a full-scene walk.  These rays do
+// occur: a zero interpolated normal makes the dielectric branch's refract() return vec3(0) (renderer.hpp:233),
+// whose Ray ctor normalisation is NaN (ray.hpp:12).
+__device__ __forceinline__ bool ray_has_nan(const RayQ& r) {
+    const float inf = B2PT_INF;
+    return !((fabsf(r.o.x) < inf) & (fabsf(r.o.y) < inf) & (fabsf(r.o.z) < inf) &
+             (fabsf(r.d.x) < inf) & (fabsf(r.d.y) < inf) & (fabsf(r.d.z) < inf));
+}
+
 __device__ __forceinline__ bool box_pass(float4 lo, float4 hi, const RayQ& r, float T, float& entry) {
     float tmin = B2PT_TMIN, tmax = T;
     slab_axis(lo.x, hi.x, r.o.x, r.invD.x, tmin, tmax);
@@ -55,7 +76,7 @@ __device__ __forceinline__ bool tri_fetch_test(const DeviceScene& S, int i, cons
 // t = +inf and takes a triangle iff its t is strictly smaller (first wins inside a leaf, :88).
 __device__ __forceinline__ void closest_exact_dfs(const DeviceScene& S, const RayQ& r, HitRec& out) {
     out.t = B2PT_INF; out.tri = -1; out.u = 0.0f; out.v = 0.0f;
-    if (S.nnodes == 0) return;
+    if (S.nnodes == 0 || ray_has_nan(r)) return;
     float tmax = r.T0;          // ray.tMax, shrunk globally (bvh.hpp:90)
     int stack[48];
     int sp = 0;
@@ -151,7 +172,7 @@ template <bool COUNT>
 __device__ __forceinline__ bool closest_octet(const DeviceScene& S, const OctetCtx& g, const RayQ& r, HitRec& out,
                                               unsigned& n_nodes, unsigned& n_tris) {
     out.t = B2PT_INF; out.tri = -1; out.u = 0.0f; out.v = 0.0f;
-    if (S.nwide == 0) return true;
+    if (S.nwide == 0 || ray_has_nan(r)) return true;
     bool tie = false, overflow = false;
     float cull = r.T0;
     int sp = 0;
@@ -231,7 +252,7 @@ __device__ __forceinline__ bool closest_octet(const DeviceScene& S, const OctetC
 // Occlusion query, cooperative.  Returns 1 occluded, 0 free, -1 stack overflow (caller must use the exact path).
 template <bool COUNT>
 __device__ __forceinline__ int any_octet(const DeviceScene& S, const OctetCtx& g, const RayQ& r, unsigned& n_nodes, unsigned& n_tris) {
-    if (S.nwide == 0) return 0;
+    if (S.nwide == 0 || ray_has_nan(r)) return 0;
     int sp = 0;
     uint32_t cur = 0;
     while (true) {

@@ -24,7 +24,7 @@ template <bool COUNT>
 __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r, HitRec& out,
                                              unsigned& n_nodes, unsigned& n_tris) {
     out.t = B2PT_INF; out.tri = -1; out.u = 0.0f; out.v = 0.0f;
-    if (S.nwide == 0) return true;
+    if (S.nwide == 0 || ray_has_nan(r)) return true;   // NaN ray: a miss in the reference (traverse.cuh)
     bool tie = false;
     float best = B2PT_INF;        // t of the current best candidate
     float cull = r.T0;            // entry distances above this cannot matter
@@ -111,7 +111,7 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
 // reference leaf box passes the slab test at T0 and which Triangle::intersect accepts in [tMin, T0].
 template <bool COUNT>
 __device__ __forceinline__ bool any_rtc(const DeviceScene& S, const RayQ& r, unsigned& n_nodes, unsigned& n_tris) {
-    if (S.nwide == 0) return false;
+    if (S.nwide == 0 || ray_has_nan(r)) return false;
     uint32_t scode[B2PT_RTC_STACK];
     int sp = 0;
     uint32_t cur = 0;

@@ -40,6 +40,7 @@ struct LaneState {
     int tri_next, tri_end; // triangles of the current leaf still to test
     bool tie;
     bool overflow;
+    bool dead;             // NaN ray: finished before it starts, result = miss (traverse.cuh, ray_has_nan)
     LaneStack stack;       // (child code, entry distance bits)
 };
 
@@ -52,6 +53,7 @@ __device__ __forceinline__ void lane_begin(LaneState& st, const RayQ& r) {
     st.tri_next = st.tri_end = 0;
     st.tie = false;
     st.overflow = false;
+    st.dead = ray_has_nan(r);
 }
 
 // Expands wide node st.cur: slab-tests the 8 children at T0 and pushes the survivors sorted by entry
@@ -117,6 +119,7 @@ __device__ __forceinline__ bool lane_pop(LaneState& st) {
 // One bounded step of a closest-hit query.  Returns true when the traversal is finished.
 template <bool COUNT, int TPS>
 __device__ __forceinline__ bool lane_closest_step(const DeviceScene& S, LaneState& st, unsigned& n_nodes, unsigned& n_tris) {
+    if (st.dead) return true;
     if (st.tri_next < st.tri_end) {
 #pragma unroll
         for (int k = 0; k < TPS; ++k) {
@@ -156,6 +159,7 @@ __device__ __forceinline__ bool lane_certify(const DeviceScene& S, const LaneSta
 // & free, 3 = stack overflow (caller must use the exact recursion).
 template <bool COUNT, int TPS>
 __device__ __forceinline__ int lane_any_step(const DeviceScene& S, LaneState& st, unsigned& n_nodes, unsigned& n_tris) {
+    if (st.dead) return 2;
     if (st.tri_next < st.tri_end) {
 #pragma unroll
         for (int k = 0; k < TPS; ++k) {

@@ -112,6 +112,35 @@ def test_axis_aligned_geometry_reference_quirks(engine):
     assert engine.stats()["shadow_rays"] == len(o2)
 
 
+@pytest.mark.parametrize("flags", [0, pt.FLAG_OCTET, pt.FLAG_EXACT_ONLY])
+def test_nonfinite_rays_are_misses(built, flags):
+    """NaN / infinite rays (zero or denormal directions normalise to NaN / inf, ray.hpp:12) are misses in the
+    reference after a full-tree walk; the kernels answer at once and must not follow EMPTY child slots.  A scene
+    of 2500 triangles has wide nodes with empty slots (10-triangle subtrees)."""
+    eng = pt.Engine(flags=flags)
+    pos = scenes.random_soup(2500, 21)
+    P = PortOracle(pos)
+    upload(eng, P)
+    o, d = rays(64000, 9)
+    nan, inf = np.float32(np.nan), np.float32(np.inf)
+    d[0::8] = 0.0                       # normalize(0) = NaN
+    d[1::8] = [1e-30, 2e-30, -1e-30]    # |d|^2 underflows: direction becomes +-inf
+    d[2::8, 1] = nan
+    o[3::8, 0] = nan
+    o[4::8, 2] = inf
+    o[5::8] = [-inf, inf, nan]
+    d[6::8] = [1e-30, 0.0, 0.0]         # (inf, NaN, NaN)
+    tri, t, uv = eng.trace_closest(o, d)
+    rt, rtt, _ = P.trace_closest(o, d)
+    assert np.array_equal(tri, rt) and np.array_equal(bits(t), bits(rtt))
+    bad = np.ones(len(o), bool); bad[7::8] = False
+    assert (tri[bad] == -1).all() and (tri[~bad] >= 0).any()
+    tm = np.full(len(o), 0.9, np.float32)
+    occ = eng.trace_any(o, d, tm)
+    assert np.array_equal(occ, P.trace_any(o, d, tm)) and not occ[bad].any()
+    eng.close()
+
+
 def test_exact_only_kernel_agrees(built):
     """B2PT_FLAG_EXACT_ONLY routes everything through the flattened reference recursion."""
     eng = pt.Engine(flags=pt.FLAG_EXACT_ONLY)

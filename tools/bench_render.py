@@ -9,7 +9,7 @@ ap = argparse.ArgumentParser(add_help=False)
 ap.add_argument("--scene", default="cornell"); ap.add_argument("--tris", type=int, default=1_000_000)
 ap.add_argument("-w", type=int, default=1920); ap.add_argument("-h", type=int, default=1080)
 ap.add_argument("-s", type=int, default=16); ap.add_argument("-b", type=int, default=5); ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--max-paths", type=int, default=8 << 20); ap.add_argument("--tag", default="")
+ap.add_argument("--max-paths", type=int, default=8 << 20); ap.add_argument("--tag", default=""); ap.add_argument("--seed", type=int, default=1)
 a = ap.parse_args()
 sc = pt.Scene()
 if a.scene == "cornell":
@@ -24,7 +24,7 @@ d_rgb = torch.empty(a.w * a.h * 3, dtype=torch.float32, device="cuda:0")
 torch.cuda.synchronize()
 best = None
 for r in range(a.reps + 1):
-    eng.render_device(pt.Camera().c, a.w, a.h, a.s, a.b, d_rgb.data_ptr(), seed=1)
+    eng.render_device(pt.Camera().c, a.w, a.h, a.s, a.b, d_rgb.data_ptr(), seed=a.seed)
     st = eng.stats()
     if r and (best is None or st["gpu_seconds"] < best["gpu_seconds"]):
         best = st
