@@ -62,6 +62,28 @@ __device__ __forceinline__ bool box_pass(float4 lo, float4 hi, const RayQ& r, fl
     return tmax > tmin;
 }
 
+// Latency hints (ncu: long-scoreboard is the top stall of every traversal kernel on the 1M-triangle scene;
+// a leaf's triangles span 3-4 cache lines that the test loop would otherwise miss on one after the other).
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// Lines 2.. of a leaf's triangle run (the loop's first load fetches line 1 itself).
+__device__ __forceinline__ void prefetch_leaf_rest(const DeviceScene& S, int first, int cnt) {
+    const char* b = reinterpret_cast<const char*>(S.tri + 3ll * first);
+    const int bytes = cnt * 48;
+    if (bytes > 128) prefetch_l1(b + 128);
+    if (bytes > 256) prefetch_l1(b + 256);
+    prefetch_l1(b + bytes - 16);
+}
+// What a stack entry will touch first when it is popped: an inner node's 224 B or a leaf's first triangles.
+__device__ __forceinline__ void prefetch_child(const DeviceScene& S, uint32_t code) {
+    if (code & B2PT_CHILD_LEAF) {
+        prefetch_l1(S.tri + 3ll * (code & 0x0FFFFFFF));
+    } else {
+        const char* b = reinterpret_cast<const char*>(S.wide + code);
+        prefetch_l1(b);
+        prefetch_l1(b + 208);
+    }
+}
+
 __device__ __forceinline__ bool tri_fetch_test(const DeviceScene& S, int i, const RayQ& r, float tmax, float& t, float& u, float& v) {
     float4 a = __ldg(&S.tri[3ll * i + 0]);
     float4 b = __ldg(&S.tri[3ll * i + 1]);
