@@ -123,7 +123,7 @@ def cpu_render(sc, W, H, spp, bounces, workload, window=None):
     return secs, (x1 - x0) * (y1 - y0) * spp, "port", oracle.PortOracle.max_threads(), rays
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, rank, world, emit):
     """--impl reference: the reference's own CPU path, rank 0 only."""
     if rank != 0:
         return 0
@@ -159,7 +159,7 @@ def reference_arm(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-paths", type=int, default=8 << 20)
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (reported in config.spp)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 0)   # the contract asks for >= 3; honour the flag but it is the caller's call
@@ -180,9 +181,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     if args.impl == "reference":
-        return reference_arm(args, rank, world)
+        return reference_arm(args, rank, world, emit)
 
     import torch
     import torch.distributed as dist
@@ -196,9 +204,13 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     W, H, SPP, B, desc = WORKLOADS[args.workload]
+    if args.spp > 0:
+        SPP = args.spp
+        desc += f" (spp overridden to {SPP})"
     sc = make_scene(args.workload)
     cam = pt.Camera()
     eng = pt.Engine(device=local_rank, max_paths=args.max_paths)
@@ -358,7 +370,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
