@@ -87,6 +87,29 @@ def test_render_independent_of_chunking_and_partition(built, cornell):
     small.close()
 
 
+def test_degenerate_normals_produce_nan_rays_not_faults(engine):
+    """Glass whose vertex normals cancel: the shading normal is NaN, the dielectric branch's refract() returns
+    vec3(0) and the Ray ctor normalises it to NaN (renderer.hpp:214-246, ray.hpp:12).  The reference traces that
+    NaN ray (a miss); the engine must return the same image without walking into empty BVH slots (this used to
+    be an illegal memory access at BASELINE configs[2] size)."""
+    ms = scenes.mesh_scene(6000, seed=5)
+    nrm = ms["nrm"].copy()
+    mat = ms["mat"].copy()
+    glass = int(np.flatnonzero(ms["materials8"][:, 0] == scenes.DIELECTRIC)[0])
+    sel = np.arange(0, len(mat), 3)
+    mat[sel] = glass
+    nrm[sel, 3:6] = -nrm[sel, 0:3]      # n1 = -n0, n2 = 0: the interpolated normal vanishes along an edge
+    nrm[sel, 6:9] = 0.0
+    nrm[sel[::2]] = 0.0                 # and everywhere on every other one
+    P = PortOracle(ms["pos"], nrm, mat, ms["materials8"])
+    pos, n2, m2 = P.triangles()
+    engine.upload_scene(pos, n2, m2, ms["materials8"])
+    cam = pt.Camera()
+    fb = engine.render(cam.c, 128, 72, 6, 8, seed=3)
+    ofb, _, _ = P.render(cam13_of(cam), 128, 72, 6, 8, seed=3)
+    assert np.array_equal(bits(fb), bits(ofb))
+
+
 def test_invalid_material_id_is_magenta(engine):
     """renderer.hpp:141-148: a hit whose material id is out of range returns (1, 0, 1)."""
     # tilted: an axis-aligned (flat-box) triangle would be invisible to the reference (aabb.hpp:21)
