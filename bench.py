@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--max-paths", type=int, default=8 << 20)
+    ap.add_argument("--max-paths", type=int, default=32 << 20)
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (reported in config.spp)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -97,7 +97,7 @@ int b2pt_create(const b2pt_config* cfg, b2pt_ctx** out) {
     ctx->device = dev;
     ctx->flags = cfg ? cfg->flags : 0;
     ctx->sm_count = prop.multiProcessorCount;
-    ctx->max_paths = (cfg && cfg->max_paths_in_flight > 0) ? cfg->max_paths_in_flight : (int64_t)(4 << 20);
+    ctx->max_paths = (cfg && cfg->max_paths_in_flight > 0) ? cfg->max_paths_in_flight : (int64_t)(16 << 20);   // larger wavefronts amortise the kernels' tails: 1M-triangle render 150 (2M) / 185 (8M) / 194 (16M) Msamples/s
     auto fail = [&](cudaError_t err, const char* what) {
         cuda_fail(nullptr, err, what, __FILE__, __LINE__);
         delete ctx;
