@@ -326,14 +326,19 @@ def main():
         k_rays, k_secs, k_launches, io = agg["extend_rays"], agg["extend_seconds"], agg["extend_launches"], 32 + 16
     bytes_per_ray = io + nodes_per_ray * info["wide_node_bytes"] + tris_per_ray * info["tri_bytes"]
     achieved = k_rays * bytes_per_ray / max(k_secs, 1e-12) * 1e-9
-    traffic, traffic_src = None, None
+    traffic, traffic_src, issue = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.max_paths == (32 << 20) and args.spp == 0:   # captured at this batch size
         tj = json.load(open(tpath)).get(args.workload, {}).get(dominant)
         if tj:
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            # what actually bounds the kernel: warp-instruction issue (4 schedulers x 148 SMs x SM clock)
+            issue = {"warp_instructions_per_launch": tj["warp_instructions_per_launch"], "issue_active_pct_ncu": tj["issue_active_pct"],
+                     "active_lanes_per_instruction_ncu": tj["active_lanes_per_instruction"],
+                     "achieved_gwarp_inst_per_s": tj["warp_instructions_per_launch"] / max(k_secs / max(k_launches, 1), 1e-12) * 1e-9,
+                     "peak_gwarp_inst_per_s": 148 * 4 * 1.965}
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": k_rays * bytes_per_ray / max(k_launches, 1),
+                "traffic": traffic, "traffic_source": traffic_src, "issue": issue, "algorithmic_bytes_per_launch": k_rays * bytes_per_ray / max(k_launches, 1),
                 "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "tris_per_ray": tris_per_ray, "kernel_ms_per_launch": 1e3 * k_secs / max(k_launches, 1), "kernel_launches": k_launches,
                 "kernel_share_of_step": k_secs / max(dev_s, 1e-12),
@@ -341,7 +346,7 @@ def main():
                         "fetch counts from the counting build of the same kernels on a 1/16-size frame. frac > 1 means the node/triangle "
                         "fetches are served by L1/L2, not HBM (the whole BVH of this workload is cache resident; compare `traffic`, the "
                         "DRAM bytes ncu measured per launch): the kernel is then bound by instruction issue, not by the memory roofline "
-                        "(ncu: profiles/r01_ncu_c2_batch_v6.txt, issue slots 83 % busy)"}
+                        "(ncu: profiles/r01_ncu_c2_batch_v8.txt, issue slots 82 % busy; see `issue`)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -359,7 +364,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": desc, "width": W, "height": H, "spp": spp_total, "bounces": B, "triangles": int(len(sc.pos)),
                    "parallelism": parallelism, "max_paths_in_flight": args.max_paths,
-                   "l2": "256 MB buffer written between timed iterations (L2 flush); per-batch path state (~1 GB) also exceeds L2"},
+                   "l2": "256 MB buffer written between timed iterations (L2 flush); per-batch path state (GBs) also exceeds L2"},
         "mrays_per_s": rays / wall * 1e-6, "rays_per_sample": rays / samples, "device_ms_per_step": 1e3 * dev_s / args.steps,
         "extend_ms_per_step": 1e3 * agg["extend_seconds"] / args.steps, "shadow_ms_per_step": 1e3 * agg["shadow_seconds"] / args.steps,
         "fallback_rays_per_step": agg["fallback_rays"] / args.steps, "build_ms": 1e3 * build_s,
