@@ -87,6 +87,37 @@ def test_render_independent_of_chunking_and_partition(built, cornell):
     small.close()
 
 
+def test_render_edge_cases(engine, cornell):
+    """Empty scene (every path misses: black, renderer.hpp:135-137), a scene without lights (paths bounce but add
+    nothing), a frame lit by six lights instead of the reference's four, tiny frames — all bit-equal to the oracle."""
+    cam = pt.Camera()
+    engine.upload_scene(np.zeros((0, 9), np.float32))
+    fb = engine.render(cam.c, 32, 18, 2, 3, seed=1)
+    assert fb.shape == (18, 32, 3) and not fb.any()
+    assert engine.stats()["extend_rays"] == 32 * 18 * 2 and engine.stats()["shadow_rays"] == 0
+    sc = cornell
+    P = PortOracle(*prebuild_from_scene(sc), sc.materials8)
+    engine.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, [])
+    fb = engine.render(cam.c, 48, 27, 2, 4, seed=2)
+    assert not fb.any() and engine.stats()["shadow_rays"] == 0
+    lights = list(sc.lights) + [((0.5, 2.5, -1.0), (1.0, 0.5, 0.25), 3.0), ((-2.0, 1.0, 2.5), (0.2, 0.4, 1.0), 5.0)]
+    engine.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, lights)
+    fb = engine.render(cam.c, 48, 27, 3, 4, seed=3)
+    l7 = np.float32([list(p) + list(c) + [i] for (p, c, i) in lights])
+    P6 = PortOracle(*prebuild_from_scene(sc), sc.materials8, lights7=l7)
+    ofb, _, _ = P6.render(cam13_of(cam), 48, 27, 3, 4, seed=3)
+    assert np.array_equal(bits(fb), bits(ofb)) and fb.mean() > 1e-3
+    engine.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
+    for (W, H) in [(2, 2), (3, 2), (2, 5)]:
+        fb = engine.render(cam.c, W, H, 4, 3, seed=9)
+        ofb, _, _ = P.render(cam13_of(cam), W, H, 4, 3, seed=9)
+        assert np.array_equal(bits(fb), bits(ofb)), (W, H)
+    # u = (x + xi) / (W - 1) (renderer.hpp:63) divides by zero for a 1-pixel-wide frame: refused, not rendered
+    for (W, H) in [(1, 1), (2, 1), (1, 4)]:
+        with pytest.raises(pt.B2ptError, match="width/height"):
+            engine.render(cam.c, W, H, 4, 3, seed=9)
+
+
 def test_degenerate_normals_produce_nan_rays_not_faults(engine):
     """Glass whose vertex normals cancel: the shading normal is NaN, the dielectric branch's refract() returns
     vec3(0) and the Ray ctor normalises it to NaN (renderer.hpp:214-246, ray.hpp:12).  The reference traces that
