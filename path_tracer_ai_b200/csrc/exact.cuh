@@ -89,6 +89,15 @@ __host__ __device__ __forceinline__ void slab_axis(float lo, float hi, float o, 
     tmax = fminf(tmax, t1);
 }
 
+// The same axis with the planes already ordered along the ray: `near` is the bound the reference ends up using
+// for tMin (lo if invD >= 0, hi if invD < 0 — its swap, aabb.hpp:17) and `far` the one for tMax.  Selecting the
+// PLANE by the ray's sign once per node (an address offset) instead of swapping the two products per child gives
+// bit-identical t values and removes two selects per axis and child.
+__host__ __device__ __forceinline__ void slab_axis_nf(float near_, float far_, float o, float invD, float& tmin, float& tmax) {
+    tmin = fmaxf(tmin, B2PT_MUL(B2PT_SUB(near_, o), invD));
+    tmax = fminf(tmax, B2PT_MUL(B2PT_SUB(far_, o), invD));
+}
+
 // Full reference slab test; returns pass and the entry distance (the running tMin after 3 axes).
 __host__ __device__ __forceinline__ bool slab_test(const float lo[3], const float hi[3], V3 o, V3 invD, float T, float& entry) {
     float tmin = B2PT_TMIN, tmax = T;

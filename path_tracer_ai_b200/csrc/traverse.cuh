@@ -84,6 +84,30 @@ __device__ __forceinline__ void prefetch_child(const DeviceScene& S, uint32_t co
     }
 }
 
+// Children 4k..4k+3 of a wide node, planes ordered along the ray: WideNode is lox|loy|loz|hix|hiy|hiz (8 floats
+// each = two float4), so the near plane of axis a is float4 index 2a + (invD[a] < 0 ? 6 : 0) + k and the far plane
+// the other one.  Slab-tests the four boxes at T0; pass[s] / tmin[s] per child.
+struct Node4 { float tmin[4]; bool pass[4]; uint32_t code[4]; };
+__device__ __forceinline__ void node_test4(const WideNode* nd, int k, const RayQ& r, Node4& out) {
+    const float4* p = reinterpret_cast<const float4*>(nd);
+    const int nx = r.invD.x < 0.0f ? 6 : 0, ny = r.invD.y < 0.0f ? 6 : 0, nz = r.invD.z < 0.0f ? 6 : 0;
+    const float4 a = __ldg(p + nx + k), b = __ldg(p + 2 + ny + k), c = __ldg(p + 4 + nz + k);
+    const float4 d = __ldg(p + 6 - nx + k), e = __ldg(p + 8 - ny + k), f = __ldg(p + 10 - nz + k);
+    const uint4 cc = __ldg(reinterpret_cast<const uint4*>(nd->child) + k);
+    const float nxs[4] = {a.x, a.y, a.z, a.w}, nys[4] = {b.x, b.y, b.z, b.w}, nzs[4] = {c.x, c.y, c.z, c.w};
+    const float fxs[4] = {d.x, d.y, d.z, d.w}, fys[4] = {e.x, e.y, e.z, e.w}, fzs[4] = {f.x, f.y, f.z, f.w};
+    out.code[0] = cc.x; out.code[1] = cc.y; out.code[2] = cc.z; out.code[3] = cc.w;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float tmin = B2PT_TMIN, tmax = r.T0;
+        slab_axis_nf(nxs[s], fxs[s], r.o.x, r.invD.x, tmin, tmax);
+        slab_axis_nf(nys[s], fys[s], r.o.y, r.invD.y, tmin, tmax);
+        slab_axis_nf(nzs[s], fzs[s], r.o.z, r.invD.z, tmin, tmax);
+        out.tmin[s] = tmin;
+        out.pass[s] = tmax > tmin;
+    }
+}
+
 __device__ __forceinline__ bool tri_fetch_test(const DeviceScene& S, int i, const RayQ& r, float tmax, float& t, float& u, float& v) {
     float4 a = __ldg(&S.tri[3ll * i + 0]);
     float4 b = __ldg(&S.tri[3ll * i + 1]);

@@ -42,40 +42,21 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
         if (!(cur & B2PT_CHILD_LEAF)) {
             const WideNode* nd = &S.wide[cur];
             if (COUNT) ++n_nodes;
-            // 8 children, SoA: 16-byte loads
-            float lox[8], loy[8], loz[8], hix[8], hiy[8], hiz[8];
-            uint32_t code[8];
-            {
-                const float4* p = reinterpret_cast<const float4*>(nd);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    float4 a = __ldg(p + 0 + k), b = __ldg(p + 2 + k), c = __ldg(p + 4 + k);
-                    float4 d = __ldg(p + 6 + k), e = __ldg(p + 8 + k), f = __ldg(p + 10 + k);
-                    lox[4 * k] = a.x; lox[4 * k + 1] = a.y; lox[4 * k + 2] = a.z; lox[4 * k + 3] = a.w;
-                    loy[4 * k] = b.x; loy[4 * k + 1] = b.y; loy[4 * k + 2] = b.z; loy[4 * k + 3] = b.w;
-                    loz[4 * k] = c.x; loz[4 * k + 1] = c.y; loz[4 * k + 2] = c.z; loz[4 * k + 3] = c.w;
-                    hix[4 * k] = d.x; hix[4 * k + 1] = d.y; hix[4 * k + 2] = d.z; hix[4 * k + 3] = d.w;
-                    hiy[4 * k] = e.x; hiy[4 * k + 1] = e.y; hiy[4 * k + 2] = e.z; hiy[4 * k + 3] = e.w;
-                    hiz[4 * k] = f.x; hiz[4 * k + 1] = f.y; hiz[4 * k + 2] = f.z; hiz[4 * k + 3] = f.w;
-                }
-                const uint4* q = reinterpret_cast<const uint4*>(nd->child);
-                uint4 c0 = __ldg(q), c1 = __ldg(q + 1);
-                code[0] = c0.x; code[1] = c0.y; code[2] = c0.z; code[3] = c0.w;
-                code[4] = c1.x; code[5] = c1.y; code[6] = c1.z; code[7] = c1.w;
-            }
-            // test all 8, push hits in insertion-sorted order (farthest deepest)
+            // 8 children in two halves; push hits in insertion-sorted order (farthest deepest)
             int base = sp;
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                float tmin = B2PT_TMIN, tmax = r.T0;
-                slab_axis(lox[s], hix[s], r.o.x, r.invD.x, tmin, tmax);
-                slab_axis(loy[s], hiy[s], r.o.y, r.invD.y, tmin, tmax);
-                slab_axis(loz[s], hiz[s], r.o.z, r.invD.z, tmin, tmax);
-                if (tmax > tmin && tmin <= cull) {
-                    // insert so that entries in [base, sp) are sorted by decreasing entry distance
-                    int j = sp++;
-                    while (j > base && sent[j - 1] < tmin) { sent[j] = sent[j - 1]; scode[j] = scode[j - 1]; --j; }
-                    sent[j] = tmin; scode[j] = code[s];
+            for (int k = 0; k < 2; ++k) {
+                Node4 n4;
+                node_test4(nd, k, r, n4);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const float tmin = n4.tmin[s];
+                    if (n4.pass[s] && tmin <= cull) {
+                        // insert so that entries in [base, sp) are sorted by decreasing entry distance
+                        int j = sp++;
+                        while (j > base && sent[j - 1] < tmin) { sent[j] = sent[j - 1]; scode[j] = scode[j - 1]; --j; }
+                        sent[j] = tmin; scode[j] = n4.code[s];
+                    }
                 }
             }
         } else {
@@ -126,24 +107,13 @@ __device__ __forceinline__ bool any_rtc(const DeviceScene& S, const RayQ& r, uns
         if (!(cur & B2PT_CHILD_LEAF)) {
             const WideNode* nd = &S.wide[cur];
             if (COUNT) ++n_nodes;
-            const float4* p = reinterpret_cast<const float4*>(nd);
-            const uint4* q = reinterpret_cast<const uint4*>(nd->child);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                float4 a = __ldg(p + 0 + k), b = __ldg(p + 2 + k), c = __ldg(p + 4 + k);
-                float4 d = __ldg(p + 6 + k), e = __ldg(p + 8 + k), f = __ldg(p + 10 + k);
-                uint4 cc = __ldg(q + k);
-                const float lx[4] = {a.x, a.y, a.z, a.w}, ly[4] = {b.x, b.y, b.z, b.w}, lz[4] = {c.x, c.y, c.z, c.w};
-                const float hx[4] = {d.x, d.y, d.z, d.w}, hy[4] = {e.x, e.y, e.z, e.w}, hz[4] = {f.x, f.y, f.z, f.w};
-                const uint32_t cd[4] = {cc.x, cc.y, cc.z, cc.w};
+                Node4 n4;
+                node_test4(nd, k, r, n4);
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    float tmin = B2PT_TMIN, tmax = r.T0;
-                    slab_axis(lx[s], hx[s], r.o.x, r.invD.x, tmin, tmax);
-                    slab_axis(ly[s], hy[s], r.o.y, r.invD.y, tmin, tmax);
-                    slab_axis(lz[s], hz[s], r.o.z, r.invD.z, tmin, tmax);
-                    if (tmax > tmin) scode[sp++] = cd[s];
-                }
+                for (int s = 0; s < 4; ++s)
+                    if (n4.pass[s]) scode[sp++] = n4.code[s];
             }
         } else {
             int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;

@@ -62,28 +62,19 @@ template <bool ANY, bool COUNT>
 __device__ __forceinline__ void lane_node_step(const DeviceScene& S, LaneState& st, unsigned& n_nodes) {
     const WideNode* nd = &S.wide[st.cur];
     if (COUNT) ++n_nodes;
-    const float4* p = reinterpret_cast<const float4*>(nd);
-    const uint4* q = reinterpret_cast<const uint4*>(nd->child);
     if (st.sp + 8 > B2PT_TSTACK) { st.overflow = true; return; }
     const int base = st.sp;
     int sp = st.sp;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        float4 a = __ldg(p + 0 + k), b = __ldg(p + 2 + k), c = __ldg(p + 4 + k);
-        float4 d = __ldg(p + 6 + k), e = __ldg(p + 8 + k), f = __ldg(p + 10 + k);
-        uint4 cc = __ldg(q + k);
-        const float lx[4] = {a.x, a.y, a.z, a.w}, ly[4] = {b.x, b.y, b.z, b.w}, lz[4] = {c.x, c.y, c.z, c.w};
-        const float hx[4] = {d.x, d.y, d.z, d.w}, hy[4] = {e.x, e.y, e.z, e.w}, hz[4] = {f.x, f.y, f.z, f.w};
-        const uint32_t cd[4] = {cc.x, cc.y, cc.z, cc.w};
+        Node4 n4;
+        node_test4(nd, k, st.r, n4);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            float tmin = B2PT_TMIN, tmax = st.r.T0;
-            slab_axis(lx[s], hx[s], st.r.o.x, st.r.invD.x, tmin, tmax);
-            slab_axis(ly[s], hy[s], st.r.o.y, st.r.invD.y, tmin, tmax);
-            slab_axis(lz[s], hz[s], st.r.o.z, st.r.invD.z, tmin, tmax);
+            const float tmin = n4.tmin[s];
             if (ANY) {
-                if (tmax > tmin) st.stack.set(sp++, make_uint2(cd[s], 0u));
-            } else if (tmax > tmin && tmin <= st.cull) {
+                if (n4.pass[s]) st.stack.set(sp++, make_uint2(n4.code[s], 0u));
+            } else if (n4.pass[s] && tmin <= st.cull) {
                 int j = sp++;
                 while (j > base) {
                     uint2 prev = st.stack.get(j - 1);
@@ -91,7 +82,7 @@ __device__ __forceinline__ void lane_node_step(const DeviceScene& S, LaneState& 
                     st.stack.set(j, prev);
                     --j;
                 }
-                st.stack.set(j, make_uint2(cd[s], __float_as_uint(tmin)));
+                st.stack.set(j, make_uint2(n4.code[s], __float_as_uint(tmin)));
             }
         }
     }

@@ -20,6 +20,7 @@ ap.add_argument("--soup", action="store_true", help="random triangle soup instea
 ap.add_argument("--coherent", action="store_true", help="camera-like primary rays instead of random rays")
 ap.add_argument("--out", default="")
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--sort", default="", help="reorder the batch before tracing: octant | morton (origin cell + direction octant)")
 args = ap.parse_args()
 
 t0 = time.time()
@@ -45,6 +46,19 @@ if args.coherent:
     d = np.stack([u.ravel() * 0.5, v.ravel() * 0.5 - 0.04, -np.ones(n, np.float32)], 1).astype(np.float32)
 else:
     o, d = scenes.random_rays(n, ms["lo"], ms["hi"], 99)
+if args.sort:
+    octant = ((d[:, 0] < 0).astype(np.int64) | ((d[:, 1] < 0).astype(np.int64) << 1) | ((d[:, 2] < 0).astype(np.int64) << 2))
+    key = octant
+    if args.sort == "morton":
+        lo_, hi_ = o.min(0), o.max(0)
+        q = np.clip(((o - lo_) / (hi_ - lo_) * 32).astype(np.int64), 0, 31)   # 32^3 origin cells
+        cell = np.zeros(n, np.int64)
+        for b in range(5):
+            for a in range(3):
+                cell |= ((q[:, a] >> b) & 1) << (3 * b + a)
+        key = (cell << 3) | octant
+    perm = np.argsort(key, kind="stable")
+    o, d = np.ascontiguousarray(o[perm]), np.ascontiguousarray(d[perm])
 dev = torch.device("cuda:0")
 to, td = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
 tri = torch.empty(n, dtype=torch.int32, device=dev); tt = torch.empty(n, dtype=torch.float32, device=dev)
