@@ -209,9 +209,6 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
     }
 }
 
-#ifndef B2PT_SHD_MINB
-#define B2PT_SHD_MINB 10
-#endif
 #ifndef B2PT_EXT_MINB
 #define B2PT_EXT_MINB 10
 #endif
@@ -292,7 +289,7 @@ __global__ void __launch_bounds__(128, B2PT_EXT_MINB) k_extend_rtc(DeviceScene S
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, B2PT_SHD_MINB) k_shadow_rtc(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
+__global__ void __launch_bounds__(128) k_shadow_rtc(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
     const int nl = S.nlight;
     const int total = W.counters[C_SHADOW];
     int j = blockIdx.x * blockDim.x + threadIdx.x;
