@@ -120,7 +120,7 @@ void b2pt_destroy(b2pt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
-    for (int i = 0; i < 16; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < B2PT_SCRATCH_SLOTS; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_fallback_count) cudaFree(ctx->d_fallback_count);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -14,6 +14,7 @@
 // test" is monotone from any reference leaf up through every wide ancestor.
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "ctx.cuh"
@@ -127,18 +128,10 @@ __global__ void k_fill_wide(const int* __restrict__ wide_src, const uint32_t* __
     }
 }
 
-template <typename T>
-int dev_alloc(b2pt_ctx* ctx, T** out, size_t count) {
-    void* p = nullptr;
-    B2PT_CUDA(ctx, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-    ctx->scene_allocs.push_back(p);
-    *out = static_cast<T*>(p);
-    return B2PT_OK;
-}
-
 }  // namespace
 
 void free_scene(b2pt_ctx* ctx) {
+    // scene buffers are persistent scratch slots of the context (freed by b2pt_destroy); only forget the scene
     for (void* p : ctx->scene_allocs) cudaFree(p);
     ctx->scene_allocs.clear();
     ctx->has_scene = false;
@@ -157,16 +150,35 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
     DeviceScene S{};
     S.ntri = ntri;
 
+    // Every device buffer of the scene and of its staging is a persistent grow-only allocation of the context
+    // (scratch slots 16..31): re-uploading a scene of the same size — the reference's GPU branch uploads once per
+    // run, an interactive caller once per frame — costs no cudaMalloc/cudaFree (measured: 0.12-3.7 s per upload of
+    // 1M triangles with them, next to a 5 GB wavefront allocation).
+    enum { SL_TRI = 16, SL_NRM, SL_NODE_LO, SL_NODE_HI, SL_LEAF_LO, SL_LEAF_HI, SL_INFO, SL_WIDE, SL_MATS,
+           SL_POS, SL_NIN, SL_MAT, SL_IDS, SL_WSRC, SL_WCHILD };
+    static_assert(SL_WCHILD < B2PT_SCRATCH_SLOTS, "scratch slots");
+
+    // The topology of the reference tree and of its collapse depends on the triangle COUNT only: it is laid out on
+    // the host once per count and its device copies (node_info, wide sources/codes, per-depth id lists) are reused.
+    b2pt_ctx::Topology& T = ctx->topo;
+    const bool topo_cached = T.valid && T.ntri == ntri;
+    if (!topo_cached) {
+        T = b2pt_ctx::Topology{};
+        T.ntri = ntri;
+        std::vector<int4>& info = T.info;
+        std::vector<int>& wide_src = T.wide_src;
+        std::vector<uint32_t>& wide_child = T.wide_child;
+        int& nleaves = T.nleaves;
+        int& maxdepth = T.maxdepth;
     // ---- host: topology of the reference tree and of its 8-ary collapse -------------------------
     std::vector<HostNode> nodes;
-    int nleaves = 0;
     if (ntri > 0) {
         nodes.reserve(static_cast<size_t>(ntri) / 2 + 16);
         layout_tree(0, ntri, 0, nodes, nleaves);
     }
     const int nnodes = static_cast<int>(nodes.size());
-    std::vector<int4> info(nnodes);
-    int maxdepth = 0;
+    info.assign(nnodes, int4{});
+    maxdepth = 0;
     for (int i = 0; i < nnodes; ++i) {
         info[i] = make_int4(nodes[i].start, nodes[i].end, nodes[i].right, nodes[i].leaf);
         maxdepth = std::max(maxdepth, nodes[i].depth);
@@ -176,8 +188,6 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
     for (int i = 0; i < nnodes; ++i) if (nodes[i].leaf < 0) by_depth[nodes[i].depth].push_back(i);
 
     // wide collapse: BFS over wide nodes; each adopts descendants three binary levels down.
-    std::vector<int> wide_src;         // 8 per wide node: reference node index or -1
-    std::vector<uint32_t> wide_child;  // 8 per wide node: child code
     std::vector<int> wide_of;          // reference node -> wide node index (for inner children), filled lazily
     if (nnodes > 0) {
         std::vector<int> queue;   // reference node index of each wide node, in wide order
@@ -223,54 +233,65 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
             }
         }
     }
+        // inner nodes by depth, deepest first, flattened: the bottom-up box pass launches one kernel per span
+        for (int dpt = maxdepth; dpt >= 0; --dpt) {
+            T.spans.push_back({T.ids_flat.size(), by_depth[dpt].size()});
+            T.ids_flat.insert(T.ids_flat.end(), by_depth[dpt].begin(), by_depth[dpt].end());
+        }
+        T.nnodes = nnodes;
+        T.valid = true;
+    }
+    const int nnodes = T.nnodes, nleaves = T.nleaves;
+    const std::vector<int4>& info = T.info;
+    const std::vector<int>& wide_src = T.wide_src;
+    const std::vector<uint32_t>& wide_child = T.wide_child;
     const int nwide = static_cast<int>(wide_src.size() / 8);
     S.nnodes = nnodes; S.nleaves = nleaves; S.nwide = nwide;
 
-    // ---- device allocations --------------------------------------------------------------------------
+    // ---- device buffers ------------------------------------------------------------------------------
     float4 *d_tri, *d_nrm, *d_node_lo, *d_node_hi, *d_leaf_lo, *d_leaf_hi;
     int4* d_info; WideNode* d_wide; DMaterial* d_mats;
     int rc;
-    if ((rc = dev_alloc(ctx, &d_tri, 3ull * ntri))) return rc;
-    if ((rc = dev_alloc(ctx, &d_nrm, 3ull * ntri))) return rc;
-    if ((rc = dev_alloc(ctx, &d_node_lo, nnodes))) return rc;
-    if ((rc = dev_alloc(ctx, &d_node_hi, nnodes))) return rc;
-    if ((rc = dev_alloc(ctx, &d_leaf_lo, nleaves))) return rc;
-    if ((rc = dev_alloc(ctx, &d_leaf_hi, nleaves))) return rc;
-    if ((rc = dev_alloc(ctx, &d_info, nnodes))) return rc;
-    if ((rc = dev_alloc(ctx, &d_wide, nwide))) return rc;
-    if ((rc = dev_alloc(ctx, &d_mats, nmat))) return rc;
+    auto reserve = [&](int slot, size_t bytes, auto** out) {
+        void* p = nullptr;
+        int r = scratch_reserve(ctx, slot, std::max<size_t>(bytes, 16), &p);
+        *out = static_cast<std::remove_reference_t<decltype(**out)>*>(p);
+        return r;
+    };
+    if ((rc = reserve(SL_TRI, sizeof(float4) * 3ull * ntri, &d_tri))) return rc;
+    if ((rc = reserve(SL_NRM, sizeof(float4) * 3ull * ntri, &d_nrm))) return rc;
+    if ((rc = reserve(SL_NODE_LO, sizeof(float4) * (size_t)nnodes, &d_node_lo))) return rc;
+    if ((rc = reserve(SL_NODE_HI, sizeof(float4) * (size_t)nnodes, &d_node_hi))) return rc;
+    if ((rc = reserve(SL_LEAF_LO, sizeof(float4) * (size_t)nleaves, &d_leaf_lo))) return rc;
+    if ((rc = reserve(SL_LEAF_HI, sizeof(float4) * (size_t)nleaves, &d_leaf_hi))) return rc;
+    if ((rc = reserve(SL_INFO, sizeof(int4) * (size_t)nnodes, &d_info))) return rc;
+    if ((rc = reserve(SL_WIDE, sizeof(WideNode) * (size_t)nwide, &d_wide))) return rc;
+    if ((rc = reserve(SL_MATS, sizeof(DMaterial) * (size_t)std::max(nmat, 1), &d_mats))) return rc;
 
-    // staging (freed at the end of the call)
     float *d_pos = nullptr, *d_nin = nullptr; int32_t* d_mat = nullptr; int *d_ids = nullptr, *d_wsrc = nullptr; uint32_t* d_wchild = nullptr;
-    auto cleanup = [&]() { cudaFree(d_pos); cudaFree(d_nin); cudaFree(d_mat); cudaFree(d_ids); cudaFree(d_wsrc); cudaFree(d_wchild); };
+    auto cleanup = [&]() {};
 #define STAGE(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); cuda_fail(ctx, e__, #call, __FILE__, __LINE__); return B2PT_ERR_CUDA; } } while (0)
     if (ntri > 0) {
-        STAGE(cudaMalloc(&d_pos, 9ull * ntri * sizeof(float)));
+        if ((rc = reserve(SL_POS, 9ull * ntri * sizeof(float), &d_pos))) return rc;
         STAGE(cudaMemcpyAsync(d_pos, pos, 9ull * ntri * sizeof(float), cudaMemcpyHostToDevice, st));
         if (nrm) {
-            STAGE(cudaMalloc(&d_nin, 9ull * ntri * sizeof(float)));
+            if ((rc = reserve(SL_NIN, 9ull * ntri * sizeof(float), &d_nin))) return rc;
             STAGE(cudaMemcpyAsync(d_nin, nrm, 9ull * ntri * sizeof(float), cudaMemcpyHostToDevice, st));
         }
         if (mat) {
-            STAGE(cudaMalloc(&d_mat, 1ull * ntri * sizeof(int32_t)));
+            if ((rc = reserve(SL_MAT, 1ull * ntri * sizeof(int32_t), &d_mat))) return rc;
             STAGE(cudaMemcpyAsync(d_mat, mat, 1ull * ntri * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         }
-        STAGE(cudaMemcpyAsync(d_info, info.data(), sizeof(int4) * nnodes, cudaMemcpyHostToDevice, st));
-        STAGE(cudaMalloc(&d_wsrc, sizeof(int) * wide_src.size()));
-        STAGE(cudaMalloc(&d_wchild, sizeof(uint32_t) * wide_child.size()));
-        STAGE(cudaMemcpyAsync(d_wsrc, wide_src.data(), sizeof(int) * wide_src.size(), cudaMemcpyHostToDevice, st));
-        STAGE(cudaMemcpyAsync(d_wchild, wide_child.data(), sizeof(uint32_t) * wide_child.size(), cudaMemcpyHostToDevice, st));
-        size_t ninner = 0;
-        std::vector<int> ids_flat;
-        std::vector<std::pair<size_t, size_t>> spans;   // per depth (deepest first): offset, count
-        for (int dpt = maxdepth; dpt >= 0; --dpt) {
-            spans.push_back({ids_flat.size(), by_depth[dpt].size()});
-            ids_flat.insert(ids_flat.end(), by_depth[dpt].begin(), by_depth[dpt].end());
-        }
-        ninner = ids_flat.size();
-        if (ninner) {
-            STAGE(cudaMalloc(&d_ids, sizeof(int) * ninner));
-            STAGE(cudaMemcpyAsync(d_ids, ids_flat.data(), sizeof(int) * ninner, cudaMemcpyHostToDevice, st));
+        const size_t ninner = T.ids_flat.size();
+        if ((rc = reserve(SL_WSRC, sizeof(int) * wide_src.size(), &d_wsrc))) return rc;
+        if ((rc = reserve(SL_WCHILD, sizeof(uint32_t) * wide_child.size(), &d_wchild))) return rc;
+        if ((rc = reserve(SL_IDS, sizeof(int) * std::max<size_t>(ninner, 1), &d_ids))) return rc;
+        if (!topo_cached || !T.on_device) {
+            STAGE(cudaMemcpyAsync(d_info, info.data(), sizeof(int4) * nnodes, cudaMemcpyHostToDevice, st));
+            STAGE(cudaMemcpyAsync(d_wsrc, wide_src.data(), sizeof(int) * wide_src.size(), cudaMemcpyHostToDevice, st));
+            STAGE(cudaMemcpyAsync(d_wchild, wide_child.data(), sizeof(uint32_t) * wide_child.size(), cudaMemcpyHostToDevice, st));
+            if (ninner) STAGE(cudaMemcpyAsync(d_ids, T.ids_flat.data(), sizeof(int) * ninner, cudaMemcpyHostToDevice, st));
+            T.on_device = true;
         }
 
         // ---- device build, timed -----------------------------------------------------------------
@@ -279,7 +300,7 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
         k_pack_triangles<<<(ntri + B - 1) / B, B, 0, st>>>(d_pos, d_nin, d_mat, ntri, d_tri, d_nrm);
         k_leaf_boxes<<<(nnodes + B - 1) / B, B, 0, st>>>(d_pos, d_info, nnodes, d_node_lo, d_node_hi, d_leaf_lo, d_leaf_hi, d_tri);
         int launches = 2;
-        for (auto& sp : spans) {
+        for (auto& sp : T.spans) {
             if (!sp.second) continue;
             k_inner_boxes<<<(static_cast<int>(sp.second) + B - 1) / B, B, 0, st>>>(d_ids + sp.first, static_cast<int>(sp.second), d_info, d_node_lo, d_node_hi);
             ++launches;
@@ -304,7 +325,6 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
         ctx->stats.build_seconds = ms * 1e-3;
     }
 #undef STAGE
-    cleanup();
 
     S.tri = d_tri; S.nrm = d_nrm; S.node_lo = d_node_lo; S.node_hi = d_node_hi; S.node_info = d_info;
     S.leaf_lo = d_leaf_lo; S.leaf_hi = d_leaf_hi; S.wide = d_wide; S.mats = d_mats; S.nmat = nmat; S.nlight = nlight;

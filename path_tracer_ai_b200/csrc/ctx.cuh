@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b2pt.h"
@@ -65,6 +66,7 @@ struct TraceCounters { unsigned long long fallback, node_fetches, tri_fetches, p
 }  // namespace b2pt
 
 // ---- host context -----------------------------------------------------------------------------------
+#define B2PT_SCRATCH_SLOTS 32   // 0..15: per-call scratch (trace / render), 16..31: scene buffers and upload staging
 struct b2pt_ctx {
     int device = 0;
     int flags = 0;
@@ -78,8 +80,17 @@ struct b2pt_ctx {
     // owned device allocations of the scene
     std::vector<void*> scene_allocs;
     // scratch (grown on demand)
-    void* scratch[16] = {};
-    size_t scratch_bytes[16] = {};
+    void* scratch[B2PT_SCRATCH_SLOTS] = {};
+    size_t scratch_bytes[B2PT_SCRATCH_SLOTS] = {};
+    // host topology of the reference tree + collapse, cached by triangle count (build.cu)
+    struct Topology {
+        bool valid = false, on_device = false;
+        int ntri = -1, nnodes = 0, nleaves = 0, maxdepth = 0;
+        std::vector<int4> info;
+        std::vector<int> wide_src, ids_flat;
+        std::vector<uint32_t> wide_child;
+        std::vector<std::pair<size_t, size_t>> spans;
+    } topo;
     b2pt::TraceCounters* d_counters = nullptr;
     int* d_fallback_count = nullptr;
     b2pt_stats stats{};
