@@ -166,16 +166,18 @@ __device__ __forceinline__ void block_append(int* counter, int* queue, bool pred
 // light-major — (light, warp, lane) — so consecutive entries are neighbouring vertices aiming at the same
 // light (coherent warps in the shadow kernels), and the runs of one vertex group sit next to each other (their
 // g0/g1 are fetched from DRAM once).
+template <int WARPS>
 __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p, int nlight) {
     constexpr int MAXROWS = 3 + B2PT_MAX_LIGHTS;
-    __shared__ int s_cnt[MAXROWS * B2PT_BIN_WARPS + 1];
+    static_assert(MAXROWS * WARPS <= 160, "the scan below covers 5 entries per lane");
+    __shared__ int s_cnt[MAXROWS * WARPS + 1];
     __shared__ int s_base[4];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nrows = 3 + nlight, n = nrows * B2PT_BIN_WARPS;
+    const int nrows = 3 + nlight, n = nrows * WARPS;
     const unsigned rowbits = (e.m0 ? 1u : 0u) | (e.m1 ? 2u : 0u) | (e.m2 ? 4u : 0u) | (e.lights << 3);
     for (int r = 0; r < nrows; ++r) {
         unsigned b = __ballot_sync(0xffffffffu, (rowbits >> r) & 1u);
-        if (lane == 0) s_cnt[r * B2PT_BIN_WARPS + w] = __popc(b);
+        if (lane == 0) s_cnt[r * WARPS + w] = __popc(b);
     }
     __syncthreads();
     if (w == 0) {
@@ -192,8 +194,8 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
         if (lane == 31) s_cnt[n] = incl;
         __syncwarp();
         if (lane < 4) {
-            int start = s_cnt[min(lane * B2PT_BIN_WARPS, n)];
-            int end = lane < 3 ? s_cnt[min((lane + 1) * B2PT_BIN_WARPS, n)] : s_cnt[n];
+            int start = s_cnt[min(lane * WARPS, n)];
+            int end = lane < 3 ? s_cnt[min((lane + 1) * WARPS, n)] : s_cnt[n];
             int cnt = end - start;
             int base = cnt ? atomicAdd(&W.counters[lane < 3 ? C_MAT0 + lane : C_SHADOW], cnt) : 0;
             s_base[lane] = base - start;
@@ -203,7 +205,7 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
     for (int r = 0; r < nrows; ++r) {
         unsigned b = __ballot_sync(0xffffffffu, (rowbits >> r) & 1u);
         if ((rowbits >> r) & 1u) {
-            int at = s_base[min(r, 3)] + s_cnt[r * B2PT_BIN_WARPS + w] + __popc(b & ((1u << lane) - 1u));
+            int at = s_base[min(r, 3)] + s_cnt[r * WARPS + w] + __popc(b & ((1u << lane) - 1u));
             if (r < 3) W.q_mat[r][at] = p; else W.q_shadow[at] = p * nlight + (r - 3);
         }
     }
@@ -261,14 +263,24 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_extend(int refill_min, DeviceSc
 }
 
 // Run-to-completion variants for coherent batches (traverse_rtc.cuh): one thread per queue entry.
-template <bool COUNT>
+// The closest-hit kernel also runs the per-vertex epilogue of its certified rays (hit point, shading normal,
+// material, light culling, binning — hit_epilogue + bin_path): the hit record never goes through HBM and the
+// bandwidth-bound epilogue overlaps other warps' traversal.  Uncertified rays get theirs in k_extend_fallback.
+// FUSED = false: the hit record is written and k_hitinfo does the rest.  Measured: fusing wins on scenes whose
+// traversal is short and uniform (Cornell 769 -> 790 Msamples/s) and loses where ray costs vary (1M mesh 217 -> 206:
+// the block-wide binning makes finished warps wait for the block's slowest ray), so render_frame fuses only small
+// trees.
+template <bool COUNT, bool FUSED>
 __global__ void __launch_bounds__(128, B2PT_EXT_MINB) k_extend_rtc(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
                                                     int P, TraceCounters* __restrict__ tc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int total = list ? *count_ptr : P;
+    if (blockIdx.x * blockDim.x >= total) return;   // whole block beyond the queue (uniform)
     unsigned n_nodes = 0, n_tris = 0;
+    Epilogue e{false, false, false, 0u};
+    int p = 0;
     if (k < total) {
-        int p = list ? list[k] : k;
+        p = list ? list[k] : k;
         float4 o4 = W.ro[p], d4 = W.rd[p];
         RayQ r;
         r.o = f4v(o4); r.d = f4v(d4);
@@ -276,9 +288,11 @@ __global__ void __launch_bounds__(128, B2PT_EXT_MINB) k_extend_rtc(DeviceScene S
         r.T0 = B2PT_INF;
         HitRec h;
         bool ok = closest_rtc<COUNT>(S, r, h, n_nodes, n_tris);
-        W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+        if (!FUSED) W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+        else if (ok) e = hit_epilogue(S, W, p, r.o, r.d, h);
         if (!ok) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
     }
+    if (FUSED) bin_path<4>(W, e, p, S.nlight);
     if (COUNT) {
         for (int off = 16; off > 0; off >>= 1) {
             n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
@@ -316,6 +330,7 @@ __global__ void __launch_bounds__(128) k_shadow_rtc(DeviceScene S, Wave W, Trace
 }
 
 // The rays the cooperative kernel could not certify: the flattened reference recursion, one thread per ray.
+template <bool FUSED>
 __global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) {
     int total = W.counters[C_FALLBACK];
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
@@ -327,7 +342,17 @@ __global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) 
         r.T0 = B2PT_INF;
         HitRec h;
         closest_exact_dfs(S, r, h);
-        W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+        if (!FUSED) {
+            W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+        } else {
+            // the epilogue k_extend_rtc runs for certified rays; a handful of rays per frame, plain atomics
+            Epilogue e = hit_epilogue(S, W, p, r.o, r.d, h);
+            if (e.m0) W.q_mat[0][atomicAdd(&W.counters[C_MAT0], 1)] = p;
+            if (e.m1) W.q_mat[1][atomicAdd(&W.counters[C_MAT1], 1)] = p;
+            if (e.m2) W.q_mat[2][atomicAdd(&W.counters[C_MAT2], 1)] = p;
+            for (int l = 0; l < S.nlight; ++l)
+                if ((e.lights >> l) & 1u) W.q_shadow[atomicAdd(&W.counters[C_SHADOW], 1)] = p * S.nlight + l;
+        }
     }
 }
 
@@ -344,7 +369,7 @@ __global__ void __launch_bounds__(B2PT_BIN_BLOCK) k_hitinfo(DeviceScene S, Wave 
         h.t = h4.x; h.tri = __float_as_int(h4.y); h.u = h4.z; h.v = h4.w;
         e = hit_epilogue(S, W, p, f4v(o4), f4v(d4), h);
     }
-    bin_path(W, e, p, S.nlight);
+    bin_path<B2PT_BIN_WARPS>(W, e, p, S.nlight);
 }
 
 // material.hpp:28-42
@@ -701,6 +726,8 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     // points and mode 1 wins in every rendered scene tried; the persistent kernels win only on unordered ray
     // batches (b2pt_trace_*: 2.1 vs 1.0 Grays/s on random rays in 1M triangles).
     const int force_mode = std::getenv("B2PT_WF_MODE") ? std::atoi(std::getenv("B2PT_WF_MODE")) : 1;
+    // closest-hit kernel with the per-vertex epilogue fused in: small trees only (see k_extend_rtc); B2PT_FUSE=0/1 forces
+    const bool fused = std::getenv("B2PT_FUSE") ? std::atoi(std::getenv("B2PT_FUSE")) != 0 : S.nwide <= 64;
     const int coherent_nodes = std::getenv("B2PT_COHERENT_NODES") ? std::atoi(std::getenv("B2PT_COHERENT_NODES")) : 512;
     int64_t launches = 0, n_extend = 0, n_shadow = 0;
     float extend_ms = 0.0f, shadow_ms = 0.0f;
@@ -738,8 +765,13 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 // run-to-completion kernels, incoherent ones the persistent kernels with lane refill.
                 const bool coherent = force_mode == 1 || (force_mode == 0 && (depth == 0 || S.nwide <= coherent_nodes));
                 if (coherent) {
-                    if (count) k_extend_rtc<true><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    else k_extend_rtc<false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    if (fused) {
+                        if (count) k_extend_rtc<true, true><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                        else k_extend_rtc<false, true><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    } else {
+                        if (count) k_extend_rtc<true, false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                        else k_extend_rtc<false, false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    }
                 } else {
                     unsigned egrid = (unsigned)std::min<long long>(((long long)P + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (long long)ctx->sm_count * 12);
                     if (count) k_extend<true, 4><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
@@ -747,10 +779,16 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                     else k_extend<false, 4><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 }
                 dbg("k_extend", pix_begin, sb, depth);
-                k_extend_fallback<<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
-                dbg("k_extend_fallback", pix_begin, sb, depth);
-                k_hitinfo<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
-                dbg("k_hitinfo", pix_begin, sb, depth);
+                if (coherent && fused) {   // k_extend_rtc has already run the epilogue of its certified rays
+                    k_extend_fallback<true><<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
+                    dbg("k_extend_fallback", pix_begin, sb, depth);
+                } else {
+                    k_extend_fallback<false><<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
+                    dbg("k_extend_fallback", pix_begin, sb, depth);
+                    k_hitinfo<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
+                    dbg("k_hitinfo", pix_begin, sb, depth);
+                    ++launches;
+                }
                 k_after_extend<<<1, 1, 0, stream>>>(Wv, S.nlight);
                 ev();
                 ++n_extend;
@@ -772,7 +810,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 dbg("k_shadow", pix_begin, sb, depth);
                 int nxt = cur ^ 1;
                 k_shade<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
-                launches += 6;
+                launches += 5;
                 dbg("k_shade", pix_begin, sb, depth);
             }
             k_resolve<<<(npc + 255) / 256, 256, 0, stream>>>(Wv, (float4*)accum, pix_begin, npc, ns);
