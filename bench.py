@@ -346,7 +346,7 @@ def main():
                         "fetch counts from the counting build of the same kernels on a 1/16-size frame. frac > 1 means the node/triangle "
                         "fetches are served by L1/L2, not HBM (the whole BVH of this workload is cache resident; compare `traffic`, the "
                         "DRAM bytes ncu measured per launch): the kernel is then bound by instruction issue, not by the memory roofline "
-                        "(ncu: profiles/r01_ncu_c2_batch_v8.txt, issue slots 82 % busy; see `issue`)"}
+                        "(ncu: profiles/r01_ncu_c2_batch_v10.txt, issue slots 82 % busy; see `issue`)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
