@@ -281,12 +281,13 @@ def main():
     e0 = time.perf_counter()
     e_steps = max(1, min(args.steps, 2))
     for _ in range(e_steps):
-        r.uploadScene(sc)
-        fb = r.render(cam, part)
-        if world > 1:   # host framebuffers are combined on rank 0 through NCCL from a device copy
-            t = torch.from_numpy(fb).to(dev)
-            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
-            fb = t.cpu().numpy()
+        r.uploadScene(sc)                       # host scene -> device (H2D inside the timed region)
+        if world == 1:
+            fb = r.render(cam, part)            # device -> host framebuffer (D2H inside the timed region)
+        else:
+            # each rank renders its share on the device, ONE NCCL sum-reduce, rank 0 copies the frame to the host
+            D.render_distributed(r.engine, cam.c, W, H, spp_total, B, d_rgb, part, seed=1234)
+            fb = d_rgb.cpu().numpy() if rank == 0 else None
     barrier()
     e1 = time.perf_counter()
     e_wall = e1 - e0
