@@ -23,6 +23,10 @@ namespace b2pt {
 
 namespace {
 
+#ifndef B2PT_SORT_CHILDREN
+#define B2PT_SORT_CHILDREN 0
+#endif
+
 struct HostNode { int start, end, right, leaf, depth; };
 
 // Host: topology of the implicit reference tree in DFS pre-order.
@@ -106,25 +110,50 @@ __global__ void k_inner_boxes(const int* __restrict__ ids, int n, const int4* __
     node_hi[i] = make_float4(gmax(c.x, d.x), gmax(c.y, d.y), gmax(c.z, d.z), 0.0f);
 }
 
-// Fills the wide nodes: slot s of wide node w adopts reference node wide_src[8*w+s] (or is empty).
+// Fills the wide nodes: wide node w adopts the reference nodes wide_src[8*w .. 8*w+7] (-1 = none).  One thread
+// per wide node.  B2PT_SORT_CHILDREN=1 stores the children by decreasing box surface area (slot order is free:
+// closest-hit kernels sort by entry distance, occlusion kernels visit the last slot first, i.e. then the most
+// compact subtree).  Measured: any-hit on random rays +5 % (5.78 -> 5.53 nodes, 6.31 -> 5.75 triangles per ray),
+// renders unchanged within noise (Cornell 793 -> 787, 1M mesh 217 -> 217): off by default.  What the Cornell frame
+// responds to is WHICH leaves are tried first (plain slot order reversed: +5 %) — an order learned from where
+// occlusions are actually found is the next step.
 __global__ void k_fill_wide(const int* __restrict__ wide_src, const uint32_t* __restrict__ wide_child, int nwide,
                             const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
                             WideNode* __restrict__ wide) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nwide * 8) return;
-    int w = g >> 3, s = g & 7;
-    int src = wide_src[g];
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwide) return;
+    int src[8];
+    uint32_t code[8];
+    float area[8];
+    for (int s = 0; s < 8; ++s) {
+        src[s] = wide_src[8 * w + s];
+        code[s] = wide_child[8 * w + s];
+        if (src[s] < 0) { area[s] = 3.402823466e+38f; continue; }
+        float4 l = node_lo[src[s]], h = node_hi[src[s]];
+        float dx = h.x - l.x, dy = h.y - l.y, dz = h.z - l.z;
+        area[s] = dx * dy + dy * dz + dz * dx;
+    }
+#if B2PT_SORT_CHILDREN
+    for (int i = 1; i < 8; ++i) {   // insertion sort, decreasing area (stable)
+        int si = src[i]; uint32_t ci = code[i]; float ai = area[i];
+        int j = i;
+        while (j > 0 && area[j - 1] < ai) { src[j] = src[j - 1]; code[j] = code[j - 1]; area[j] = area[j - 1]; --j; }
+        src[j] = si; code[j] = ci; area[j] = ai;
+    }
+#endif
     WideNode& nd = wide[w];
-    if (src < 0) {
-        // inverted box: never passes the slab test
-        nd.lox[s] = nd.loy[s] = nd.loz[s] = 3.402823466e+38f;
-        nd.hix[s] = nd.hiy[s] = nd.hiz[s] = -3.402823466e+38f;
-        nd.child[s] = B2PT_CHILD_EMPTY;
-    } else {
-        float4 l = node_lo[src], h = node_hi[src];
-        nd.lox[s] = l.x; nd.loy[s] = l.y; nd.loz[s] = l.z;
-        nd.hix[s] = h.x; nd.hiy[s] = h.y; nd.hiz[s] = h.z;
-        nd.child[s] = wide_child[g];
+    for (int s = 0; s < 8; ++s) {
+        if (src[s] < 0) {
+            // inverted box: never passes the slab test
+            nd.lox[s] = nd.loy[s] = nd.loz[s] = 3.402823466e+38f;
+            nd.hix[s] = nd.hiy[s] = nd.hiz[s] = -3.402823466e+38f;
+            nd.child[s] = B2PT_CHILD_EMPTY;
+        } else {
+            float4 l = node_lo[src[s]], h = node_hi[src[s]];
+            nd.lox[s] = l.x; nd.loy[s] = l.y; nd.loz[s] = l.z;
+            nd.hix[s] = h.x; nd.hiy[s] = h.y; nd.hiz[s] = h.z;
+            nd.child[s] = code[s];
+        }
     }
 }
 
@@ -305,7 +334,7 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
             k_inner_boxes<<<(static_cast<int>(sp.second) + B - 1) / B, B, 0, st>>>(d_ids + sp.first, static_cast<int>(sp.second), d_info, d_node_lo, d_node_hi);
             ++launches;
         }
-        k_fill_wide<<<(nwide * 8 + B - 1) / B, B, 0, st>>>(d_wsrc, d_wchild, nwide, d_node_lo, d_node_hi, d_wide);
+        k_fill_wide<<<(nwide + B - 1) / B, B, 0, st>>>(d_wsrc, d_wchild, nwide, d_node_lo, d_node_hi, d_wide);
         ++launches;
         STAGE(cudaEventRecord(ctx->ev3, st));
         STAGE(cudaGetLastError());

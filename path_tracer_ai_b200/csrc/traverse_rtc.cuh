@@ -13,6 +13,11 @@ namespace b2pt {
 #define B2PT_RTC_STACK 72
 // Explicit prefetch.global.L1 of a leaf's later cache lines and of the next stack entry: measured SLOWER (Cornell
 // 744 -> 475 Msamples/s, 1M mesh 185 -> 175): the hints are LSU instructions in kernels that are issue-bound.
+// Order in which an occlusion query visits the passing children of a node: 0 = last slot first, 1 = first slot
+// first, 2 = nearest child first (see profiles/r01_experiments.md).
+#ifndef B2PT_ANY_ORDER
+#define B2PT_ANY_ORDER 0
+#endif
 #ifndef B2PT_PREFETCH
 #define B2PT_PREFETCH 0
 #endif
@@ -107,14 +112,39 @@ __device__ __forceinline__ bool any_rtc(const DeviceScene& S, const RayQ& r, uns
         if (!(cur & B2PT_CHILD_LEAF)) {
             const WideNode* nd = &S.wide[cur];
             if (COUNT) ++n_nodes;
+#if B2PT_ANY_ORDER == 2
+            // nearest child next, the others in slot order
+            float near_t = B2PT_INF;
+            uint32_t near_code = B2PT_CHILD_EMPTY;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 Node4 n4;
                 node_test4(nd, k, r, n4);
 #pragma unroll
-                for (int s = 0; s < 4; ++s)
-                    if (n4.pass[s]) scode[sp++] = n4.code[s];
+                for (int s = 0; s < 4; ++s) {
+                    if (n4.pass[s]) {
+                        if (n4.tmin[s] < near_t) {
+                            if (near_code != B2PT_CHILD_EMPTY) scode[sp++] = near_code;
+                            near_t = n4.tmin[s]; near_code = n4.code[s];
+                        } else {
+                            scode[sp++] = n4.code[s];
+                        }
+                    }
+                }
             }
+            if (near_code != B2PT_CHILD_EMPTY) { cur = near_code; continue; }
+#else
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                Node4 n4;
+                node_test4(nd, B2PT_ANY_ORDER == 1 ? 1 - k : k, r, n4);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int ss = B2PT_ANY_ORDER == 1 ? 3 - s : s;
+                    if (n4.pass[ss]) scode[sp++] = n4.code[ss];
+                }
+            }
+#endif
         } else {
             int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;
             if (B2PT_PREFETCH) prefetch_leaf_rest(S, first, cnt);
