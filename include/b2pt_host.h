@@ -26,6 +26,11 @@ int b2pt_scene_get_triangles(const b2pt_scene* scene, float* pos, float* nrm, in
 int b2pt_scene_get_materials(const b2pt_scene* scene, b2pt_material* mats);
 int b2pt_scene_get_lights(const b2pt_scene* scene, b2pt_light* lights);
 
+/* Loader self-check: parses the OBJ twice — with the chunked multi-threaded parser (nthreads <= 0: all host
+ * threads; chunk_bytes: smallest chunk, a few bytes puts every construct on a chunk boundary) and line by line on
+ * one thread — and compares every array.  0 = identical, > 0 = which array differs first, < 0 = cannot open. */
+int b2pt_obj_parser_selfcheck(const char* path, int32_t nthreads, int64_t chunk_bytes);
+
 /* Camera(position, target, up, fov) as the reference constructs it. */
 int b2pt_camera_look_at(const float* position, const float* target, const float* up, float fov, b2pt_camera* out);
 

@@ -25,6 +25,31 @@ int b2pt_scene_load_obj(const char* path, b2pt_scene** out) {
 
 void b2pt_scene_free(b2pt_scene* s) { delete s; }
 
+int b2pt_obj_parser_selfcheck(const char* path, int32_t nthreads, int64_t chunk_bytes) {
+    if (!path) return -1;
+    b2pt::obj::Mesh a, b;
+    bool oka = b2pt::obj::parse_file(path, a, nthreads, chunk_bytes > 0 ? (size_t)chunk_bytes : (size_t)1);
+    bool okb = b2pt::obj::parse_file_serial(path, b);
+    if (oka != okb) return 1;
+    if (!oka) return a.error == b.error ? -1 : 2;
+    auto same_idx = [](const b2pt::obj::Index& x, const b2pt::obj::Index& y) {
+        return x.vertex_index == y.vertex_index && x.normal_index == y.normal_index && x.texcoord_index == y.texcoord_index;
+    };
+    auto same_bits = [](const std::vector<float>& x, const std::vector<float>& y) {
+        return x.size() == y.size() && (x.empty() || !std::memcmp(x.data(), y.data(), x.size() * sizeof(float)));
+    };
+    if (!same_bits(a.vertices, b.vertices)) return 3;
+    if (!same_bits(a.normals, b.normals)) return 4;
+    if (!same_bits(a.texcoords, b.texcoords)) return 5;
+    if (a.indices.size() != b.indices.size()) return 6;
+    for (size_t i = 0; i < a.indices.size(); ++i) if (!same_idx(a.indices[i], b.indices[i])) return 7;
+    if (a.material_ids != b.material_ids) return 8;
+    if (a.materials.size() != b.materials.size()) return 9;
+    for (size_t i = 0; i < a.materials.size(); ++i)
+        if (a.materials[i].name != b.materials[i].name || std::memcmp(a.materials[i].diffuse, b.materials[i].diffuse, 12) || a.materials[i].ior != b.materials[i].ior) return 10;
+    return 0;
+}
+
 int64_t b2pt_scene_num_triangles(const b2pt_scene* s) { return s ? (int64_t)s->scene.getTriangles().size() : 0; }
 int32_t b2pt_scene_num_materials(const b2pt_scene* s) { return s ? (int32_t)s->scene.getMaterials().size() : 0; }
 int32_t b2pt_scene_num_lights(const b2pt_scene* s) { return s ? (int32_t)s->scene.getLights().size() : 0; }

@@ -44,13 +44,15 @@ def _host_lib():
         L.b2pt_scene_get_lights.argtypes = [vp, vp]
         L.b2pt_camera_look_at.argtypes = [vp, vp, vp, C.c_float, C.POINTER(_capi.Camera)]
         L.b2pt_write_png.argtypes = [C.c_char_p, C.c_int32, C.c_int32, vp]
+        L.b2pt_obj_parser_selfcheck.argtypes = [C.c_char_p, C.c_int32, C.c_int64]
+        L.b2pt_obj_parser_selfcheck.restype = C.c_int
         L._host_ready = True
     return L
 
 
 HOST_EXPORTS = ["b2pt_scene_load_obj", "b2pt_scene_free", "b2pt_scene_num_triangles", "b2pt_scene_num_materials",
                 "b2pt_scene_num_lights", "b2pt_scene_get_triangles", "b2pt_scene_get_materials", "b2pt_scene_get_lights",
-                "b2pt_camera_look_at", "b2pt_write_png"]
+                "b2pt_camera_look_at", "b2pt_write_png", "b2pt_obj_parser_selfcheck"]
 
 
 class Camera:

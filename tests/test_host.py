@@ -83,6 +83,59 @@ def test_loader_obj_features(built, tmp_path):
     assert np.isclose((model[:, 1].max() + model[:, 1].min()) / 2, 1.8, atol=1e-5)
 
 
+def test_chunked_obj_parser_equals_line_by_line(built, tmp_path):
+    """The multi-threaded chunked parser must return exactly what a sequential read returns: relative (negative)
+    indices, `usemtl` state and `mtllib` lookups all depend on earlier lines.  Chunk sizes down to a few bytes put
+    every construct on a chunk boundary."""
+    from path_tracer_ai_b200.renderer import _host_lib
+    L = _host_lib()
+    rng = np.random.default_rng(3)
+    (tmp_path / "a.mtl").write_text("newmtl diffuse_red\nKd 0.8 0.1 0.1\nnewmtl glass_x\nKd 1 1 1\nNi 1.45\n")
+    (tmp_path / "b.mtl").write_text("# second library\nnewmtl mirror_late\nKd 0.9 0.9 0.9\nnewmtl diffuse_red\nKd 0.1 0.8 0.1\n")
+    lines = ["# generated", "usemtl diffuse_red   # used before any mtllib: not found", "mtllib a.mtl"]
+    nv = nn = nt = 0
+    for blk in range(60):
+        k = int(rng.integers(3, 9))
+        for _ in range(k):
+            x, y, z = rng.normal(size=3)
+            lines.append(f"v {x:.6f} {y:.6f} {z:.6f}" + (" 1.0" if rng.random() < 0.2 else ""))
+            nv += 1
+            if rng.random() < 0.7:
+                lines.append("vn %.4f %.4f %.4f" % tuple(rng.normal(size=3))); nn += 1
+            if rng.random() < 0.5:
+                lines.append("vt %.3f %.3f" % tuple(rng.random(2))); nt += 1
+        if blk == 20:
+            lines.append("mtllib b.mtl")
+        if rng.random() < 0.5:
+            lines.append("usemtl " + str(rng.choice(["diffuse_red", "glass_x", "mirror_late", "nope"])))
+        lines.append("g group%d" % blk)
+        for _ in range(int(rng.integers(1, 5))):
+            m = int(rng.integers(3, 6))      # triangles, quads, pentagons
+            form = int(rng.integers(0, 5))
+            toks = []
+            for _ in range(m):
+                vi = int(rng.integers(1, nv + 1)) if rng.random() < 0.5 else -int(rng.integers(1, min(nv, 6) + 1))
+                ti = (int(rng.integers(1, nt + 1)) if rng.random() < 0.5 else -1) if nt else 0
+                ni = (int(rng.integers(1, nn + 1)) if rng.random() < 0.5 else -1) if nn else 0
+                if form == 0 or (form in (1, 3) and not ti) or (form in (2, 3) and not ni): toks.append(f"{vi}")
+                elif form == 1: toks.append(f"{vi}/{ti}")
+                elif form == 2: toks.append(f"{vi}//{ni}")
+                else: toks.append(f"{vi}/{ti}/{ni}")
+            lines.append("f " + " ".join(toks))
+        if rng.random() < 0.1:
+            lines.append("f 1 2")            # malformed: skipped with a warning
+        if rng.random() < 0.1:
+            lines.append("   \t  ")
+    text = "\r\n".join(lines[:40]) + "\r\n" + "\n".join(lines[40:])   # CRLF part, LF part, no trailing newline
+    obj = tmp_path / "mix.obj"
+    obj.write_bytes(text.encode())
+    for nthreads, chunk in [(1, 1 << 20), (4, 7), (3, 64), (8, 1), (2, 333), (0, 1000)]:
+        assert L.b2pt_obj_parser_selfcheck(os.fsencode(str(obj)), nthreads, chunk) == 0, (nthreads, chunk)
+    assert L.b2pt_obj_parser_selfcheck(os.fsencode(str(tmp_path / "missing.obj")), 2, 64) < 0
+    (tmp_path / "empty.obj").write_bytes(b"")
+    assert L.b2pt_obj_parser_selfcheck(os.fsencode(str(tmp_path / "empty.obj")), 4, 1) == 0
+
+
 def test_camera_matches_oracle(built):
     cam = pt.Camera()
     want = PortOracle.camera()
