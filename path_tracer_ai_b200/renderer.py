@@ -151,6 +151,26 @@ class B200Renderer:
         self.frameBuffer = self.engine.render(camera.c, s.width, s.height, s.samplesPerPixel, s.maxBounces, self.seed, part)
         return self.frameBuffer
 
+    def renderProgressive(self, camera: Camera, samples_per_pass: int):
+        """Progressive, resumable accumulation: yields (samples_done, estimate) after every pass of
+        `samples_per_pass` samples per pixel.  Pass k renders the sample range [k*n, (k+1)*n) of the frame through
+        `b2pt_partition.sample_begin/sample_count`, so the union of the passes is exactly the sample set of the
+        one-shot frame (same Philox streams); only the order of the float additions differs.  The estimate after a
+        pass is the running mean; the last one equals render() up to that rounding."""
+        self._require("renderProgressive")
+        s = self.settings
+        total = s.samplesPerPixel
+        accum = np.zeros((s.height, s.width, 3), np.float64)
+        done = 0
+        while done < total:
+            n = min(samples_per_pass, total - done)
+            part = self.engine.render(camera.c, s.width, s.height, total, s.maxBounces, self.seed,
+                                      dict(sample_begin=done, sample_count=n))
+            accum += part.astype(np.float64) * total     # a pass returns (sum of its samples) / total
+            done += n
+            self.frameBuffer = (accum / done).astype(np.float32)
+            yield done, self.frameBuffer
+
     def tonemapped(self) -> np.ndarray:
         """Renderer::saveImage's pixel maths (src/renderer.cpp:8-17) on the host: clamp, pow(1/gamma), truncate."""
         if self.frameBuffer is None:

@@ -182,6 +182,25 @@ def test_tonemap_matches_host(engine, cornell):
     assert (px != host).mean() < 0.01
 
 
+def test_progressive_accumulation_converges_to_the_one_shot_frame(built, cornell):
+    """Passes over disjoint sample ranges add up to the one-shot frame (same Philox streams, different float
+    addition order), and every intermediate estimate is the frame a renderer with that many samples of the SAME
+    streams would average."""
+    r = pt.B200Renderer(pt.Settings(width=96, height=54, samplesPerPixel=24, maxBounces=4), seed=77)
+    r.initialize()
+    r.uploadScene(cornell)
+    cam = pt.Camera()
+    full = r.render(cam).copy()
+    seen = []
+    for done, est in r.renderProgressive(cam, 7):
+        seen.append(done)
+        assert est.shape == full.shape and np.isfinite(est).all()
+    assert seen == [7, 14, 21, 24]
+    assert np.allclose(r.frameBuffer, full, rtol=2e-5, atol=1e-7)
+    first = next(iter(r.renderProgressive(cam, 7)))[1]
+    assert not np.allclose(first, full, rtol=1e-3)        # 7 samples are not 24
+
+
 def test_b200renderer_lifecycle_and_png(built, cornell, tmp_path):
     """OptixRenderer-shaped lifecycle through the Python mirror, and the reference-compatible CLI."""
     import subprocess
