@@ -3,7 +3,8 @@
 //   -m/--mode {cpu,gpu} (gpu)  -w/--width (800)  -h/--height (450; note: -h is height, not help)
 //   -s/--samples (100)  -b/--bounces (5)  -g/--gamma (2.2)  -i/--input (IronMan/IronMan.obj)
 //   -o/--output (output.png)  --help
-// Extras: --seed N (default 1234), --device N, --dump-float FILE (raw float32 W*H*3 framebuffer).
+// Extras: --seed N (default 1234), --device N, --dump-float FILE (raw float32 W*H*3 framebuffer),
+// --camera-pos x,y,z / --camera-target x,y,z / --fov deg (defaults = the constants of src/main.cpp:46-51).
 // Same flow as src/main.cpp:39-96: Scene -> loadFromObj -> fixed Camera -> renderer -> saveImage,
 // timing uploadScene + render.  Differences, by design: --mode cpu is refused (this binary has no
 // CPU renderer; the reference CPU path lives in oracle/ as test infrastructure) and a GPU failure is
@@ -14,6 +15,7 @@
 #include <cstring>
 #include <iostream>
 #include <map>
+#include <stdexcept>
 #include <string>
 
 #include "b200_renderer.hpp"
@@ -35,6 +37,9 @@ const Opt kOpts[] = {
     {"seed", 0, true, "1234", "RNG seed (Philox key)"},
     {"device", 0, true, "0", "CUDA device ordinal"},
     {"dump-float", 0, true, "", "Also write the float framebuffer (raw float32, W*H*3)"},
+    {"camera-pos", 0, true, "0,2,5", "Camera position x,y,z (reference: fixed at 0,2,5)"},
+    {"camera-target", 0, true, "0,1.8,0", "Camera target x,y,z (reference: fixed at 0,1.8,0)"},
+    {"fov", 0, true, "45", "Vertical field of view in degrees (reference: fixed at 45)"},
     {"help", 0, false, "", "Print help"},
 };
 
@@ -102,8 +107,15 @@ int main(int argc, char* argv[]) {
         }
         std::cout << "- Total triangles: " << scene.getTriangles().size() << "\n- Total materials: " << scene.getMaterials().size() << std::endl;
 
-        // main.cpp:46-51
-        b2pt::Camera camera(b2pt::vec3(0.0f, 2.0f, 5.0f), b2pt::vec3(0.0f, 1.8f, 0.0f), b2pt::vec3(0.0f, 1.0f, 0.0f), 45.0f);
+        // main.cpp:46-51 (the defaults of the three camera options are the reference's constants)
+        auto vec3Of = [](const std::string& text, const char* name) {
+            float v[3];
+            if (std::sscanf(text.c_str(), "%f,%f,%f", &v[0], &v[1], &v[2]) != 3)
+                throw std::runtime_error(std::string("Option '") + name + "' expects x,y,z");
+            return b2pt::vec3(v[0], v[1], v[2]);
+        };
+        b2pt::Camera camera(vec3Of(args["camera-pos"], "camera-pos"), vec3Of(args["camera-target"], "camera-target"),
+                            b2pt::vec3(0.0f, 1.0f, 0.0f), static_cast<float>(std::atof(args["fov"].c_str())));
 
         b2pt::B200Renderer::Settings settings;
         settings.width = std::atoi(args["width"].c_str());
