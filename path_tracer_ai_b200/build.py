@@ -56,7 +56,9 @@ def _deps():
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale(LIB, _deps()):
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in CU_SOURCES]
+    extra = os.environ.get("B2PT_EXTRA_NVCC", "").split()   # experiments: e.g. -DB2PT_SHD_BLOCK=64
+    out = os.environ.get("B2PT_LIB_OUT", LIB)
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", out] + [os.path.join(CSRC, s) for s in CU_SOURCES]
     cmd += [os.path.join(HOST, "host_api.cpp"), "-lz"]
     if verbose:
         cmd.insert(1, "-Xptxas")
@@ -71,7 +73,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 def build_cli(force: bool = False, verbose: bool = False) -> str:

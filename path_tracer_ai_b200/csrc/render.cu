@@ -211,6 +211,16 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
     }
 }
 
+// block sizes of the two run-to-completion traversal kernels (64 / 128 / 256 measured: profiles/r01_experiments.md)
+#ifndef B2PT_EXT_BLOCK
+#define B2PT_EXT_BLOCK 128
+#endif
+#ifndef B2PT_EXT_BLOCK_FUSED
+#define B2PT_EXT_BLOCK_FUSED 256   // fused epilogue: bigger blocks bin longer runs (Cornell +1.6 %); unfused: 128 (mesh -2 % at 256)
+#endif
+#ifndef B2PT_SHD_BLOCK
+#define B2PT_SHD_BLOCK 128
+#endif
 #ifndef B2PT_EXT_MINB
 #define B2PT_EXT_MINB 10
 #endif
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_extend(int refill_min, DeviceSc
 // the block-wide binning makes finished warps wait for the block's slowest ray), so render_frame fuses only small
 // trees.
 template <bool COUNT, bool FUSED>
-__global__ void __launch_bounds__(128, B2PT_EXT_MINB) k_extend_rtc(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
+__global__ void __launch_bounds__(FUSED ? B2PT_EXT_BLOCK_FUSED : B2PT_EXT_BLOCK, (B2PT_EXT_MINB * 128) / (FUSED ? B2PT_EXT_BLOCK_FUSED : B2PT_EXT_BLOCK)) k_extend_rtc(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
                                                     int P, TraceCounters* __restrict__ tc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int total = list ? *count_ptr : P;
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(128, B2PT_EXT_MINB) k_extend_rtc(DeviceScene S
         else if (ok) e = hit_epilogue(S, W, p, r.o, r.d, h);
         if (!ok) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
     }
-    if (FUSED) bin_path<4>(W, e, p, S.nlight);
+    if (FUSED) bin_path<B2PT_EXT_BLOCK_FUSED / 32>(W, e, p, S.nlight);
     if (COUNT) {
         for (int off = 16; off > 0; off >>= 1) {
             n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(128, B2PT_EXT_MINB) k_extend_rtc(DeviceScene S
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow_rtc(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
+__global__ void __launch_bounds__(B2PT_SHD_BLOCK) k_shadow_rtc(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
     const int nl = S.nlight;
     const int total = W.counters[C_SHADOW];
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -766,11 +776,11 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 const bool coherent = force_mode == 1 || (force_mode == 0 && (depth == 0 || S.nwide <= coherent_nodes));
                 if (coherent) {
                     if (fused) {
-                        if (count) k_extend_rtc<true, true><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                        else k_extend_rtc<false, true><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                        if (count) k_extend_rtc<true, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                        else k_extend_rtc<false, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                     } else {
-                        if (count) k_extend_rtc<true, false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                        else k_extend_rtc<false, false><<<(P + 127) / 128, 128, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                        if (count) k_extend_rtc<true, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                        else k_extend_rtc<false, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                     }
                 } else {
                     unsigned egrid = (unsigned)std::min<long long>(((long long)P + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (long long)ctx->sm_count * 12);
@@ -795,9 +805,9 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 if (S.nlight > 0) {
                     ++n_shadow;
                     if (coherent) {
-                        unsigned sg = (unsigned)(((long long)P * S.nlight + 127) / 128);
-                        if (count) k_shadow_rtc<true><<<sg, 128, 0, stream>>>(S, Wv, ctx->d_counters);
-                        else k_shadow_rtc<false><<<sg, 128, 0, stream>>>(S, Wv, ctx->d_counters);
+                        unsigned sg = (unsigned)(((long long)P * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
+                        if (count) k_shadow_rtc<true><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
+                        else k_shadow_rtc<false><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
                     } else {
                         unsigned sgrid = (unsigned)std::min<long long>(((long long)P * S.nlight + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (long long)ctx->sm_count * 12);
                         if (count) k_shadow<true, 4><<<sgrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, ctx->d_counters);
