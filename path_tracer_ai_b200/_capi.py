@@ -240,9 +240,12 @@ class Engine:
         return Partition(part.get("tile_rank", 0), part.get("tile_world", 0), part.get("tile_size", 0),
                          part.get("sample_begin", 0), part.get("sample_count", 0))
 
-    def render(self, cam: Camera, width, height, spp, bounces, seed=1234, part=None):
-        """Returns fb[H, W, 3] float32, row 0 = bottom of the view (reference frameBuffer order)."""
-        fb = np.empty((height, width, 3), np.float32)
+    def render(self, cam: Camera, width, height, spp, bounces, seed=1234, part=None, out=None):
+        """Returns fb[H, W, 3] float32, row 0 = bottom of the view (reference frameBuffer order).  `out`: a
+        C-contiguous float32 array of that shape to render into (saves the page faults of a fresh 25 MB array)."""
+        if out is not None and (out.shape != (height, width, 3) or out.dtype != np.float32 or not out.flags.c_contiguous):
+            out = None
+        fb = np.empty((height, width, 3), np.float32) if out is None else out
         st = self._settings(width, height, spp, bounces)
         pt = self._partition(part)
         rc = self._L.b2pt_render(self._h, C.byref(cam), C.byref(st), seed, None if pt is None else C.byref(pt), _p(fb))

@@ -148,7 +148,9 @@ class B200Renderer:
     def render(self, camera: Camera, part=None):
         self._require("render")
         s = self.settings
-        self.frameBuffer = self.engine.render(camera.c, s.width, s.height, s.samplesPerPixel, s.maxBounces, self.seed, part)
+        # like the reference's frameBuffer member, the array is reused by the next render() of this renderer
+        self.frameBuffer = self.engine.render(camera.c, s.width, s.height, s.samplesPerPixel, s.maxBounces, self.seed, part,
+                                              out=self.frameBuffer)
         return self.frameBuffer
 
     def renderProgressive(self, camera: Camera, samples_per_pass: int):
