@@ -1,17 +1,29 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the per-pixel Monte-Carlo hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1|c2|c3|c5]
+                    [--scaling weak|strong] [--spp S] [--max-paths P] [--no-cpu-baseline]
 
 Workload (default, N=1): BASELINE.json configs[1] — the procedural Cornell box through Scene::loadFromObj,
 1920x1080, 100 spp, 5 bounces, on one B200.  One "step" = one full frame.  metric = Msamples/s (camera paths per
-second, whole job); Mrays/s is reported beside it.  N>1: one process per GPU (torchrun), WEAK scaling over sample
-ranges — the frame has 100*N spp, rank r renders samples [100r, 100(r+1)) with the scene replicated, and the
-per-rank buffers are combined by ONE NCCL sum-reduce per frame inside the timed region.  `--scaling strong` splits
-the 100-spp frame by interleaved pixel tiles instead (bit-identical image for any N).
+second, whole job); Mrays/s is reported beside it.  c1 / c3 / c5 are configs[0] / [2] / [4]; configs[3] (the
+closest-hit microbench) is tools/bench_trace.py.
 
---impl reference times the reference's own CPU renderer (oracle/_ref when present, else the oracle port) on a
-bounded sample of the same frame on all host threads.
+* value   — frames rendered with the scene resident in HBM and the frame left on the device; timed between
+            barrier + synchronize pairs (max over ranks), an L2 flush between iterations.
+* e2e     — the reference-facing call sequence with HOST buffers: B200Renderer.uploadScene + render, i.e. the
+            region src/main.cpp:87-92 times (scene H2D and framebuffer D2H inside the timed region).
+* roofline— the dominant traversal kernel: algorithmic bytes (SURVEY 8d accounting, fetch counts from the
+            instrumented build of the same kernels) over its CUDA-event time on the engine's stream, against the
+            measured HBM peak; `traffic` / `issue` are the DRAM bytes and warp-instruction figures of the committed
+            ncu capture (profiles/r01_traffic.json).
+* cpu_baseline / --impl reference — the reference's own Renderer::render (oracle/_ref, unmodified headers) on all
+            host threads, on a bounded sample of the same frame.
+
+N>1: one process per GPU (torchrun), scene replicated.  WEAK scaling (default): the frame has 100*N spp, rank r
+renders samples [100r, 100(r+1)) and the per-rank buffers are combined by ONE NCCL sum-reduce per frame inside the
+timed region.  `--scaling strong` splits the fixed frame by interleaved 1024-pixel tiles instead (bit-identical image
+for any N).
 """
 from __future__ import annotations
 
