@@ -139,6 +139,14 @@ def reference_arm(args, rank, world, emit):
     """--impl reference: the reference's own CPU path, rank 0 only."""
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is ONE process that should use every host thread
+    # it is allowed to (set before the oracle library, and with it the OpenMP runtime, is loaded).
+    if world > 1 or "TORCHELASTIC_RUN_ID" in os.environ:
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = str(ncpu)
     W, H, SPP, B, desc = WORKLOADS[args.workload]
     sc = make_scene(args.workload)
     # bounded sample per step: full resolution, a few of the frame's samples per pixel (per-sample cost is the
