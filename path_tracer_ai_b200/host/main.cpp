@@ -4,7 +4,8 @@
 //   -s/--samples (100)  -b/--bounces (5)  -g/--gamma (2.2)  -i/--input (IronMan/IronMan.obj)
 //   -o/--output (output.png)  --help
 // Extras: --seed N (default 1234), --device N, --dump-float FILE (raw float32 W*H*3 framebuffer),
-// --camera-pos x,y,z / --camera-target x,y,z / --fov deg (defaults = the constants of src/main.cpp:46-51).
+// --camera-pos x,y,z / --camera-target x,y,z / --fov deg (defaults = the constants of src/main.cpp:46-51),
+// --lights x,y,z,r,g,b,I[;...] (default = the four constants of include/scene.hpp:55-80).
 // Same flow as src/main.cpp:39-96: Scene -> loadFromObj -> fixed Camera -> renderer -> saveImage,
 // timing uploadScene + render.  Differences, by design: --mode cpu is refused (this binary has no
 // CPU renderer; the reference CPU path lives in oracle/ as test infrastructure) and a GPU failure is
@@ -17,6 +18,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "b200_renderer.hpp"
 #include "camera.hpp"
@@ -40,6 +42,7 @@ const Opt kOpts[] = {
     {"camera-pos", 0, true, "0,2,5", "Camera position x,y,z (reference: fixed at 0,2,5)"},
     {"camera-target", 0, true, "0,1.8,0", "Camera target x,y,z (reference: fixed at 0,1.8,0)"},
     {"fov", 0, true, "45", "Vertical field of view in degrees (reference: fixed at 45)"},
+    {"lights", 0, true, "", "Replace the reference's four lights: x,y,z,r,g,b,intensity[;x,y,z,...] (at most 16)"},
     {"help", 0, false, "", "Print help"},
 };
 
@@ -104,6 +107,22 @@ int main(int argc, char* argv[]) {
         if (!scene.loadFromObj(inputFile)) {
             std::cerr << "Failed to load model: " << inputFile << std::endl;   // main.cpp:40-43
             return -1;
+        }
+        if (!args["lights"].empty()) {
+            std::vector<b2pt::Light> ls;
+            const std::string& text = args["lights"];
+            for (size_t pos = 0; pos <= text.size();) {
+                size_t semi = text.find(';', pos);
+                std::string one = text.substr(pos, semi == std::string::npos ? std::string::npos : semi - pos);
+                float v[7];
+                if (std::sscanf(one.c_str(), "%f,%f,%f,%f,%f,%f,%f", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]) != 7)
+                    throw std::runtime_error("Option 'lights' expects x,y,z,r,g,b,intensity[;...]");
+                ls.emplace_back(b2pt::vec3(v[0], v[1], v[2]), b2pt::vec3(v[3], v[4], v[5]), v[6]);
+                if (semi == std::string::npos) break;
+                pos = semi + 1;
+            }
+            if (ls.size() > 16) throw std::runtime_error("Option 'lights': at most 16 lights");
+            scene.setLights(std::move(ls));
         }
         std::cout << "- Total triangles: " << scene.getTriangles().size() << "\n- Total materials: " << scene.getMaterials().size() << std::endl;
 

@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b2pt.h"
@@ -89,6 +91,9 @@ public:
         lights.emplace_back(vec3(0.0f, 2.0f, -2.0f), vec3(1.0f), 1.0f);
         lights.emplace_back(vec3(0.0f, 0.1f, 0.0f), vec3(0.9f, 0.9f, 1.0f), 2.0f);
     }
+
+    // Not in the reference (its four lights are constants, scene.hpp:55-80): replaces them (command line --lights).
+    void setLights(std::vector<Light> ls) { lights = std::move(ls); }
 
     const std::vector<std::shared_ptr<Material>>& getMaterials() const { return materials; }
     const std::vector<Light>& getLights() const { return lights; }

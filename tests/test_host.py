@@ -192,6 +192,14 @@ def test_cli_contract(built, tmp_path):
     assert r.returncode != 0 and "Failed to load model" in r.stderr
     r = subprocess.run([cli(), "--frobnicate"], capture_output=True, text=True)
     assert r.returncode != 0
+    # extras beyond the reference's flags: camera / light overrides are validated before any GPU work
+    for flag in ("--seed", "--camera-pos", "--camera-target", "--fov", "--lights", "--dump-float"):
+        assert flag in subprocess.run([cli(), "--help"], capture_output=True, text=True).stdout
+    obj = scenes.write_cornell_obj(str(tmp_path))
+    r = subprocess.run([cli(), "-i", obj, "--lights", "1,2,3"], capture_output=True, text=True)
+    assert r.returncode != 0 and "expects x,y,z,r,g,b,intensity" in r.stderr
+    r = subprocess.run([cli(), "-i", obj, "--camera-pos", "north"], capture_output=True, text=True)
+    assert r.returncode != 0 and "expects x,y,z" in r.stderr
 
 
 def test_cli_without_gpu_fails_loudly(built, tmp_path):
