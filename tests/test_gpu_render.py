@@ -224,3 +224,16 @@ def test_b200renderer_lifecycle_and_png(built, cornell, tmp_path):
     cfb = np.fromfile(dump, np.float32).reshape(36, 64, 3)
     assert np.array_equal(bits(cfb), bits(fb))
     assert (tmp_path / "c.png").read_bytes() == data
+    # camera / light / seed overrides of the CLI reach the engine exactly like the Python arguments do
+    lights = [((1.0, 3.0, 1.5), (1.0, 0.8, 0.6), 7.5), ((-2.0, 1.0, 2.0), (0.3, 0.5, 1.0), 4.0)]
+    res = subprocess.run([cli, "-i", obj, "-w", "64", "-h", "36", "-s", "4", "-b", "3", "-o", str(tmp_path / "d.png"),
+                          "--dump-float", str(dump), "--seed", "99", "--camera-pos", "1.5,2.5,4.5", "--camera-target", "0,1.5,0",
+                          "--fov", "50", "--lights", ";".join(",".join(str(x) for x in (*p, *c, i)) for p, c, i in lights)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    eng = pt.Engine()
+    eng.upload_scene(cornell.pos, cornell.nrm, cornell.mat, cornell.materials8, lights)
+    efb = eng.render(pt.Camera((1.5, 2.5, 4.5), (0.0, 1.5, 0.0), fov=50.0).c, 64, 36, 4, 3, seed=99)
+    eng.close()
+    assert np.array_equal(bits(np.fromfile(dump, np.float32).reshape(36, 64, 3)), bits(efb))
+    assert not np.array_equal(bits(efb), bits(fb))
