@@ -10,7 +10,7 @@
 
 namespace b2pt {
 
-#define B2PT_RTC_STACK 72
+#define B2PT_RTC_STACK 96   // 7 pending siblings per wide level; <= 11 levels below 2^28 triangles even with misaligned subtrees
 // Explicit prefetch.global.L1 of a leaf's later cache lines and of the next stack entry: measured SLOWER (Cornell
 // 744 -> 475 Msamples/s, 1M mesh 185 -> 175): the hints are LSU instructions in kernels that are issue-bound.
 // Order in which an occlusion query visits the passing children of a node: 0 = last slot first, 1 = first slot
