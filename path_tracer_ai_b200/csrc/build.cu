@@ -239,8 +239,10 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
             for (int i = nnodes - 1; i >= 0; --i)
                 if (nodes[i].leaf < 0) height[i] = 1 + std::max(height[i + 1], height[nodes[i].right]);
             queue.push_back(0);
+            std::vector<int> wlevel(1, 0);   // wide level of each wide node (root = 0)
             for (size_t w = 0; w < queue.size(); ++w) {
                 int ref = queue[w];
+                T.max_wide_level = std::max(T.max_wide_level, wlevel[w]);
                 int cur[8], ncur = 2;
                 cur[0] = ref + 1; cur[1] = nodes[ref].right;
                 for (int level = 0; level < 2; ++level) {
@@ -258,7 +260,7 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
                     int c = cur[s];
                     wide_src.push_back(c);
                     if (nodes[c].leaf >= 0) wide_child.push_back(leaf_code(c));
-                    else { wide_child.push_back(static_cast<uint32_t>(queue.size())); queue.push_back(c); }
+                    else { wide_child.push_back(static_cast<uint32_t>(queue.size())); queue.push_back(c); wlevel.push_back(wlevel[w] + 1); }
                 }
             }
         }
@@ -270,6 +272,11 @@ int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t
         }
         T.nnodes = nnodes;
         T.valid = true;
+    }
+    if (T.max_wide_level > B2PT_MAX_WIDE_LEVEL) {
+        ctx->err = "b2pt_upload_scene: BVH deeper than the traversal stacks allow (wide level " + std::to_string(T.max_wide_level) + ")";
+        T.valid = false;
+        return B2PT_ERR_INVALID;
     }
     const int nnodes = T.nnodes, nleaves = T.nleaves;
     const std::vector<int4>& info = T.info;

@@ -31,6 +31,11 @@ struct __align__(32) WideNode {
 };
 static_assert(sizeof(WideNode) == 224, "WideNode layout");
 
+// Deepest inner wide node (root = level 0) a scene may have: the run-to-completion kernels keep at most 7 pending
+// siblings per level plus the 8 children of the node being expanded on an unchecked stack (traverse_rtc.cuh);
+// build_scene refuses deeper trees (2^28 triangles need 9-10 levels).
+#define B2PT_MAX_WIDE_LEVEL 12
+
 #define B2PT_CHILD_EMPTY 0xFFFFFFFFu
 #define B2PT_CHILD_LEAF 0x80000000u
 
@@ -85,7 +90,7 @@ struct b2pt_ctx {
     // host topology of the reference tree + collapse, cached by triangle count (build.cu)
     struct Topology {
         bool valid = false, on_device = false;
-        int ntri = -1, nnodes = 0, nleaves = 0, maxdepth = 0;
+        int ntri = -1, nnodes = 0, nleaves = 0, maxdepth = 0, max_wide_level = 0;
         std::vector<int4> info;
         std::vector<int> wide_src, ids_flat;
         std::vector<uint32_t> wide_child;

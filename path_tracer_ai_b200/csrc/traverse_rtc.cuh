@@ -15,6 +15,7 @@ namespace b2pt {
 // 744 -> 475 Msamples/s, 1M mesh 185 -> 175): the hints are LSU instructions in kernels that are issue-bound.
 // Order in which an occlusion query visits the passing children of a node: 0 = last slot first, 1 = first slot
 // first, 2 = nearest child first (see profiles/r01_experiments.md).
+static_assert(7 * B2PT_MAX_WIDE_LEVEL + 8 <= B2PT_RTC_STACK, "rtc stack must cover the deepest tree build_scene accepts");
 #ifndef B2PT_ANY_ORDER
 #define B2PT_ANY_ORDER 0
 #endif
