@@ -6,7 +6,8 @@
 //
 // Inputs: random triangles/rays over many scales, plus rays aimed at points ON the triangle's edges and
 // vertices (u = 0, v = 0, u + v = 1 up to rounding), rays with tMax set to the hit distance +/- a few ulps,
-// t near tMin, |a| near the 1e-7 threshold, and tiny/huge coordinates (underflowing numerators).
+// t near tMin, |a| near the 1e-7 threshold, tiny/huge coordinates (underflowing numerators), and for a share of
+// the boundary-aimed rays all 125 neighbours obtained by moving the origin -2..2 ulps per coordinate.
 #include <cmath>
 using std::isnan;
 using std::isinf;
@@ -86,6 +87,14 @@ int main(int argc, char** argv) {
         else if (tk == 1) tm = uni() * vlength(dir) * 2.0f;
         else if (tk >= 2 && tk <= 3 && tri_test_plain(v0, e1, e2, o, d, B2PT_INF, tt, uu, vv)) tm = ulps(tt, (int)(rnd() % 7) - 3);
         check(v0, e1, e2, o, d, tm);
+        // dense probe of the decision boundaries: the same ray with its origin moved by -2..2 ulps per coordinate
+        // (125 neighbours) — edge- and vertex-aimed rays then straddle u = 0, v = 0, u + v = 1 bit by bit
+        if (kind <= 3 && rnd() % 16 == 0) {
+            for (int ix = -2; ix <= 2; ++ix)
+                for (int iy = -2; iy <= 2; ++iy)
+                    for (int iz = -2; iz <= 2; ++iz)
+                        check(v0, e1, e2, mk3(ulps(o.x, ix), ulps(o.y, iy), ulps(o.z, iz)), d, tm);
+        }
         // the same ray started tMin away from the plane (t lands next to 0.001)
         if (rnd() % 8 == 0 && tri_test_plain(v0, e1, e2, o, d, B2PT_INF, tt, uu, vv)) {
             float back = tt - 0.001f * (1.0f + 4e-7f * sym());
