@@ -81,6 +81,10 @@ struct b2pt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::string err;
     bool has_scene = false;
+    // occluder-aware child order (build.cu learn_child_order): 0 = collect statistics during the next wavefront
+    // batch, 1 = collected (re-order before the next batch), 2 = done / off
+    int order_state = 2;
+    unsigned* d_order_stats = nullptr;   // visits[nwide*8] then hits[nwide*8]
     b2pt::DeviceScene scene{};
     // owned device allocations of the scene
     std::vector<void*> scene_allocs;
@@ -120,6 +124,9 @@ int scratch_reserve(b2pt_ctx* ctx, int slot, size_t bytes, void** out);
 int build_scene(b2pt_ctx* ctx, const float* pos, const float* nrm, const int32_t* mat, int64_t ntri,
                 const b2pt_material* mats, int32_t nmat, const b2pt_light* lights, int32_t nlight);
 void free_scene(b2pt_ctx* ctx);
+// Re-orders every wide node's child slots by the occlusion rate (hits per visit) the instrumented shadow kernel
+// measured, so that occlusion queries try the likeliest occluders first.  No effect on any result.  Synchronises.
+int learn_child_order(b2pt_ctx* ctx);
 
 // trace.cu — all pointers device; launches on ctx->stream; counters accumulate into ctx->d_counters.
 int launch_trace_closest(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n,

@@ -339,6 +339,26 @@ __global__ void __launch_bounds__(B2PT_SHD_BLOCK) k_shadow_rtc(DeviceScene S, Wa
     }
 }
 
+// Shadow kernel of the ONE statistics batch per scene (occluder-aware child order, build.cu learn_child_order): same
+// visibility bytes as k_shadow_rtc; every 64th warp also counts box passes and terminal hits per (wide node, slot).
+__global__ void __launch_bounds__(B2PT_SHD_BLOCK) k_shadow_learn(DeviceScene S, Wave W, unsigned* __restrict__ visits, unsigned* __restrict__ hits) {
+    const int nl = S.nlight;
+    const int total = W.counters[C_SHADOW];
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < total) {
+        int e = W.q_shadow[j];
+        int p = e / nl, l = e - p * nl;
+        float4 g0 = W.g0[p], g1 = W.g1[p];
+        V3 P = f4v(g0), n = f4v(g1);
+        const DLight& lt = S.lights[l];
+        V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
+        float dist = vlength(lightDir);
+        lightDir = vnormalize(lightDir);
+        RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));   // renderer.hpp:271-275
+        W.vis[e] = any_rtc_learn(S, r, ((j >> 5) & 63) == 0, visits, hits) ? 1 : 0;
+    }
+}
+
 // The rays the cooperative kernel could not certify: the flattened reference recursion, one thread per ray.
 template <bool FUSED>
 __global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) {
@@ -760,6 +780,11 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     for (long long pix_begin = 0; pix_begin < nown; pix_begin += npc_max) {
         int npc = (int)std::min<long long>(npc_max, nown - pix_begin);
         for (int sb = 0; sb < s_count; sb += ns_max) {
+            if (ctx->order_state == 1) {   // statistics of the previous batch are in: re-order the children once
+                int lrc = learn_child_order(ctx);
+                if (lrc) return lrc;
+            }
+            const bool learn_batch = ctx->order_state == 0 && !count;
             int ns = std::min(ns_max, s_count - sb);
             int P = npc * ns;
             int sabs = s_begin + sb;
@@ -804,7 +829,10 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 ++n_extend;
                 if (S.nlight > 0) {
                     ++n_shadow;
-                    if (coherent) {
+                    if (learn_batch) {
+                        unsigned sg = (unsigned)(((long long)P * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
+                        k_shadow_learn<<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_order_stats, ctx->d_order_stats + 8 * (size_t)S.nwide);
+                    } else if (coherent) {
                         unsigned sg = (unsigned)(((long long)P * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
                         if (count) k_shadow_rtc<true><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
                         else k_shadow_rtc<false><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
@@ -823,6 +851,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 launches += 5;
                 dbg("k_shade", pix_begin, sb, depth);
             }
+            if (learn_batch) ctx->order_state = 1;
             k_resolve<<<(npc + 255) / 256, 256, 0, stream>>>(Wv, (float4*)accum, pix_begin, npc, ns);
             ++launches;
             dbg("k_resolve", pix_begin, sb, -1);

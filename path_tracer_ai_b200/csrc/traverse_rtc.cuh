@@ -162,4 +162,48 @@ __device__ __forceinline__ bool any_rtc(const DeviceScene& S, const RayQ& r, uns
 }
 
 
+// ---- occlusion query with visiting statistics --------------------------------------------------------
+// The same query as any_rtc (same candidate set, same answer), instrumented for the occluder-aware child order
+// (build.cu learn_child_order): it counts how often each (wide node, slot) passes the box test of a shadow ray
+// (`visits`) and in which slot's leaf a ray was found occluded (`hits`).  Run for ONE wavefront batch per scene and
+// only by the warps that sample (`on`); the production kernel is any_rtc, untouched by this.
+__device__ __forceinline__ bool any_rtc_learn(const DeviceScene& S, const RayQ& r, bool on, unsigned* __restrict__ visits,
+                                              unsigned* __restrict__ hits) {
+    if (S.nwide == 0 || ray_has_nan(r)) return false;
+    uint32_t scode[B2PT_RTC_STACK];
+    uint32_t sslot[B2PT_RTC_STACK];   // (wide node << 3 | slot) each entry came from
+    int sp = 0;
+    uint32_t cur = 0, cur_slot = 0;
+    while (true) {
+        if (!(cur & B2PT_CHILD_LEAF)) {
+            const WideNode* nd = &S.wide[cur];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                Node4 n4;
+                node_test4(nd, k, r, n4);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if (n4.pass[s]) {
+                        const uint32_t slot = (cur << 3) | (uint32_t)(4 * k + s);
+                        if (on) atomicAdd(&visits[slot], 1u);
+                        scode[sp] = n4.code[s]; sslot[sp] = slot; ++sp;
+                    }
+                }
+            }
+        } else {
+            int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;
+            for (int i = first; i < first + cnt; ++i) {
+                float t, u, v;
+                if (tri_fetch_test(S, i, r, r.T0, t, u, v)) {
+                    if (on) atomicAdd(&hits[cur_slot], 1u);
+                    return true;
+                }
+            }
+        }
+        if (sp == 0) return false;
+        --sp;
+        cur = scode[sp]; cur_slot = sslot[sp];
+    }
+}
+
 }  // namespace b2pt
