@@ -2,12 +2,14 @@
 """bench.py — headline benchmark of the per-pixel Monte-Carlo hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1|c2|c3|c5]
-                    [--scaling weak|strong] [--spp S] [--max-paths P] [--no-cpu-baseline]
+                    [--scaling strong|weak] [--spp S] [--max-paths P] [--no-cpu-baseline] [--no-c4] [--c4-rays R]
 
-Workload (default, N=1): BASELINE.json configs[1] — the procedural Cornell box through Scene::loadFromObj,
-1920x1080, 100 spp, 5 bounces, on one B200.  One "step" = one full frame.  metric = Msamples/s (camera paths per
-second, whole job); Mrays/s is reported beside it.  c1 / c3 / c5 are configs[0] / [2] / [4]; configs[3] (the
-closest-hit microbench) is tools/bench_trace.py.
+Workload (default): BASELINE.json configs[2] — the 1M-triangle tessellated mesh scene (mixed materials, plus the 8 room
+triangles Scene::loadFromObj always adds), 1920x1080, 256 spp, 8 bounces: the configuration the north-star's
+">= 1.5 Grays/s per B200 on a 1M-triangle scene" is quoted on.  One "step" = one full frame.  metric = Msamples/s
+(camera paths per second, whole job); Mrays/s is reported beside it.  c1 / c2 / c5 are configs[0] / [1] / [4].
+configs[3] — the closest-hit microbench, 100M random rays against the 1M-triangle mesh, hit ids checked bit-for-bit
+against the reference CPU BVH on a stratified subset — runs in the same process and is reported under `c4`.
 
 * value   — frames rendered with the scene resident in HBM and the frame left on the device; timed between
             barrier + synchronize pairs (max over ranks), an L2 flush between iterations.
@@ -15,19 +17,22 @@ closest-hit microbench) is tools/bench_trace.py.
             region src/main.cpp:87-92 times (scene H2D and framebuffer D2H inside the timed region).
 * roofline— the dominant traversal kernel: algorithmic bytes (SURVEY 8d accounting, fetch counts from the
             instrumented build of the same kernels) over its CUDA-event time on the engine's stream, against the
-            measured HBM peak; `traffic` / `issue` are the DRAM bytes and warp-instruction figures of the committed
-            ncu capture (profiles/r01_traffic.json).
+            measured HBM peak.  `traffic` (DRAM bytes per launch), `frac_hbm_measured` and `issue` come from the
+            committed ncu capture (profiles/r02_traffic.json) and are only attached when that capture was taken from
+            the same kernel sources (source hash); `bound` says what actually limits the kernel.
 * cpu_baseline / --impl reference — the reference's own Renderer::render (oracle/_ref, unmodified headers) on all
             host threads, on a bounded sample of the same frame.
 
-N>1: one process per GPU (torchrun), scene replicated.  WEAK scaling (default): the frame has 100*N spp, rank r
-renders samples [100r, 100(r+1)) and the per-rank buffers are combined by ONE NCCL sum-reduce per frame inside the
-timed region.  `--scaling strong` splits the fixed frame by interleaved 1024-pixel tiles instead (bit-identical image
-for any N).
+N>1: one process per GPU (torchrun), scene replicated.  STRONG scaling (default): the fixed frame is split into
+interleaved runs of 1024 pixels (run k -> rank k mod N), every pixel is computed wholly by one rank with Philox keyed by
+(pixel, sample), and the per-rank buffers are combined by ONE NCCL sum-reduce per frame inside the timed region: the
+combined frame is bit-identical for every N (`frame_hash`).  `--scaling weak` gives every rank its own range of
+SPP samples of a frame with SPP*N samples per pixel instead.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -44,13 +49,25 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (width, height, spp, bounces, description)
-    "c1": (800, 450, 10, 5, "BASELINE configs[0]: Cornell box 800x450 10 spp 5 bounces"),
-    "c2": (1920, 1080, 100, 5, "BASELINE configs[1]: Cornell box 1920x1080 100 spp 5 bounces"),
-    "c3": (1920, 1080, 256, 8, "BASELINE configs[2]: 1M-triangle mesh scene 1920x1080 256 spp 8 bounces"),
-    "c5": (3840, 2160, 1024, 8, "BASELINE configs[4]: 10M-triangle dielectric-heavy scene 3840x2160 1024 spp 8 bounces"),
+    # name: (width, height, spp, bounces, triangles, description)
+    "c1": (800, 450, 10, 5, 0, "BASELINE configs[0]: Cornell box 800x450 10 spp 5 bounces"),
+    "c2": (1920, 1080, 100, 5, 0, "BASELINE configs[1]: Cornell box 1920x1080 100 spp 5 bounces"),
+    "c3": (1920, 1080, 256, 8, 1_000_000, "BASELINE configs[2]: 1M-triangle mesh scene 1920x1080 256 spp 8 bounces"),
+    "c5": (3840, 2160, 1024, 8, 10_000_000, "BASELINE configs[4]: 10M-triangle dielectric-heavy scene 3840x2160 1024 spp 8 bounces"),
 }
-# (configs[3], the closest-hit microbench, is tools/bench_trace.py.)
+DEFAULT_MAX_PATHS = 32 << 20
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_traffic.json")
+KERNEL_SOURCES = ["exact.cuh", "ctx.cuh", "traverse.cuh", "traverse_rtc.cuh", "traverse_thread.cuh", "render.cu", "trace.cu", "build.cu"]
+
+
+def kernel_source_hash() -> str:
+    """Hash of the kernel sources: an ncu capture is only quoted beside numbers measured from the same code."""
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        p = os.path.join(ROOT, "path_tracer_ai_b200", "csrc", f)
+        if os.path.exists(p):
+            h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
 
 
 def load_peaks():
@@ -59,6 +76,24 @@ def load_peaks():
         j = json.load(open(p))
         return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_dict(args, world, ntri):
+    """The same dict in both arms (the driver compares them)."""
+    W, H, SPP, B, _, desc = WORKLOADS[args.workload]
+    if args.spp > 0:
+        SPP = args.spp
+        desc += f" (spp overridden to {SPP})"
+    spp_total = SPP * world if args.scaling == "weak" else SPP
+    if world <= 1:
+        par = "single GPU"
+    elif args.scaling == "weak":
+        par = f"sample ranges x{world}, scene replicated, 1 NCCL reduce/frame"
+    else:
+        par = f"interleaved 1024-pixel runs x{world}, scene replicated, 1 NCCL reduce/frame"
+    return {"workload": desc, "width": W, "height": H, "spp": spp_total, "bounces": B, "triangles": int(ntri),
+            "parallelism": par, "max_paths_in_flight": args.max_paths,
+            "l2": "256 MB buffer written between timed iterations (L2 flush); per-batch path state (GBs) also exceeds L2"}
 
 
 class ClockSampler:
@@ -100,43 +135,62 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_scene(workload: str):
-    import path_tracer_ai_b200 as pt
+# ---- scenes -----------------------------------------------------------------------------------------
+def prebuild_arrays(workload: str, tmpdir: str):
+    """The workload's scene as the reference sees it BEFORE BVH::build: ('obj', path) or ('arrays', dict).  Pure
+    numpy — does not load libb2pt.so (the reference arm must not map the product library)."""
     from path_tracer_ai_b200 import scenes
-    sc = pt.Scene()
     if workload in ("c1", "c2"):
-        with tempfile.TemporaryDirectory() as tmp:
-            assert sc.loadFromObj(scenes.write_cornell_obj(tmp, seed=1234))
-    elif workload == "c3":
-        ms = scenes.mesh_scene(1_000_000, seed=1234)
-        sc.setContents(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
+        return "obj", scenes.write_cornell_obj(tmpdir, seed=1234)
+    if workload == "c3":
+        return "arrays", scenes.mesh_scene(1_000_000, seed=1234)
+    return "arrays", scenes.mesh_scene(10_000_000, seed=1234, dielectric_fraction=0.6)
+
+
+def make_scene(kind, payload):
+    import path_tracer_ai_b200 as pt
+    sc = pt.Scene()
+    if kind == "obj":
+        assert sc.loadFromObj(payload)
     else:
-        ms = scenes.mesh_scene(10_000_000, seed=1234, dielectric_fraction=0.6)
-        sc.setContents(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
+        sc.setContents(payload["pos"], payload["nrm"], payload["mat"], payload["materials8"])
     return sc
 
 
-def prebuild(sc):
-    inv = np.empty_like(sc.order)
-    inv[sc.order] = np.arange(len(sc.order), dtype=np.int32)
-    return sc.pos[inv], sc.nrm[inv], sc.mat[inv]
-
-
-def cpu_render(sc, W, H, spp, bounces, workload, window=None):
-    """Reference CPU renderer on all host threads.  Returns (seconds, samples, kind, cores, rays or None)."""
+def make_cpu_oracle(kind, payload):
+    """The reference's own CPU path on the workload's scene (oracle/_ref when built, else the in-repo port)."""
     import oracle
-    if oracle.ref_available() and window is None:
-        R = oracle.RefOracle(*prebuild(sc), sc.materials8)
-        _, secs = R.render(W, H, spp, bounces)
-        return secs, W * H * spp, "reference", oracle.RefOracle.max_threads(), None
-    P = oracle.PortOracle(*prebuild(sc), sc.materials8)
-    x0, y0, x1, y1 = window if window else (0, 0, W, H)
-    _, secs, rays = P.render(oracle.PortOracle.camera(), W, H, spp, bounces, seed=1, window=window)
-    return secs, (x1 - x0) * (y1 - y0) * spp, "port", oracle.PortOracle.max_threads(), rays
+    if oracle.ref_available():
+        R = oracle.RefOracle(obj_path=payload) if kind == "obj" else \
+            oracle.RefOracle(payload["pos"], payload["nrm"], payload["mat"], payload["materials8"])
+        return R, "reference", oracle.RefOracle.max_threads()
+    if kind == "obj":
+        import path_tracer_ai_b200 as pt   # the port has no OBJ loader of its own
+        sc = pt.Scene(); assert sc.loadFromObj(payload)
+        inv = np.empty_like(sc.order); inv[sc.order] = np.arange(len(sc.order), dtype=np.int32)
+        P = oracle.PortOracle(sc.pos[inv], sc.nrm[inv], sc.mat[inv], sc.materials8)
+    else:
+        P = oracle.PortOracle(payload["pos"], payload["nrm"], payload["mat"], payload["materials8"])
+    return P, "port", oracle.PortOracle.max_threads()
+
+
+def cpu_render(orc, kind, W, H, spp, bounces):
+    """One full-resolution CPU frame of `spp` samples per pixel.  Returns (seconds, samples)."""
+    import oracle
+    if kind == "reference":
+        _, secs = orc.render(W, H, spp, bounces)
+    else:
+        _, secs, _ = orc.render(oracle.PortOracle.camera(), W, H, spp, bounces, seed=1)
+    return secs, W * H * spp
+
+
+def cpu_sample_text(W, H, spp, SPP, B, cores, kind):
+    who = "reference Renderer::render (oracle/_ref, unmodified headers)" if kind == "reference" else "oracle port of Renderer::render"
+    return f"{W}x{H}, {spp} of {SPP} spp, {B} bounces per step; {who} on {cores} threads"
 
 
 def reference_arm(args, rank, world, emit):
-    """--impl reference: the reference's own CPU path, rank 0 only."""
+    """--impl reference: the reference's own CPU path, rank 0 only; libb2pt.so is never loaded here."""
     if rank != 0:
         return 0
     # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is ONE process that should use every host thread
@@ -147,40 +201,133 @@ def reference_arm(args, rank, world, emit):
         except AttributeError:
             ncpu = os.cpu_count() or 1
         os.environ["OMP_NUM_THREADS"] = str(ncpu)
-    W, H, SPP, B, desc = WORKLOADS[args.workload]
-    sc = make_scene(args.workload)
+    W, H, SPP, B, _, desc = WORKLOADS[args.workload]
+    if args.spp > 0:
+        SPP = args.spp
+    with tempfile.TemporaryDirectory() as tmp:
+        kind_s, payload = prebuild_arrays(args.workload, tmp)
+        orc, kind, cores = make_cpu_oracle(kind_s, payload)
+    ntri = orc.ntri
     # bounded sample per step: full resolution, a few of the frame's samples per pixel (per-sample cost is the
-    # same for every sample index); for the 1M-triangle scene a centre crop as well.
-    window = None
-    spp = 2 if args.workload != "c1" else SPP
-    if args.workload in ("c3", "c5"):
-        window = (W // 2 - 120, H // 2 - 68, W // 2 + 120, H // 2 + 68)
-        spp = 1
-    secs0, ns0, kind, cores, _ = cpu_render(sc, W, H, 1, B, args.workload, window)   # calibration (also warms caches)
-    rate = ns0 / secs0
-    target = 4.0   # seconds per step
-    per_spp = (ns0 / 1)
-    spp = max(1, min(SPP, int(rate * target / per_spp)))
-    for _ in range(args.warmup):
-        cpu_render(sc, W, H, spp, B, args.workload, window)
-    t = []
-    ns = 0
+    # same for every sample index); sized from a 1-spp calibration frame so that a step takes ~4 s.
+    secs0, ns0 = cpu_render(orc, kind, W, H, 1, B)
+    spp = max(1, min(SPP, int(4.0 / max(secs0, 1e-3))))
+    for _ in range(min(args.warmup, 1)):
+        cpu_render(orc, kind, W, H, spp, B)
+    t, ns = [], 0
     for _ in range(args.steps):
-        secs, ns, kind, cores, _ = cpu_render(sc, W, H, spp, B, args.workload, window)
+        secs, ns = cpu_render(orc, kind, W, H, spp, B)
         t.append(secs)
     ms = 1e3 * sum(t) / len(t)
     value = ns / (ms * 1e-3) * 1e-6
-    sample = f"{W}x{H}" + (f" crop {window}" if window else "") + f", {spp} of {SPP} spp, {B} bounces per step; reference Renderer::render on {cores} threads"
     line = {
         "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": desc, "width": W, "height": H, "spp": SPP, "bounces": B},
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": config_dict(args, world, ntri),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": cpu_sample_text(W, H, spp, SPP, B, cores, kind)},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
     return 0
+
+
+# ---- configs[3]: closest-hit microbench -----------------------------------------------------------------
+def c4_microbench(pt, torch, dist, dev, local_rank, rank, world, nrays, ncheck, peak, max_paths):
+    """100M random rays (origin uniform in the mesh AABB inflated 10 %, direction uniform on the sphere) against the
+    1M-triangle mesh (geometry only), rays resident in HBM, contiguous ray-range shards over the ranks.  Timed with CUDA
+    events on the engine's stream (b2pt_stats.trace_seconds), max over ranks; hit ids and t bits of a stratified subset
+    are compared with the reference CPU BVH on rank 0; a 64-bit hash of ALL ids makes runs comparable."""
+    from path_tracer_ai_b200 import scenes
+    ms = scenes.mesh_scene(1_000_000, seed=1234, room=False)
+    order = pt.reference_order(ms["pos"])
+    pos = ms["pos"][order]
+    eng = pt.Engine(device=local_rank, max_paths=max_paths)
+    eng.upload_scene(pos)
+    build_ms = eng.stats()["build_seconds"] * 1e3
+    BLK = 1_000_000
+    nblk = max(1, nrays // BLK)
+    nrays = nblk * BLK
+    b0, b1 = (nblk * rank) // world, (nblk * (rank + 1)) // world
+    n = (b1 - b0) * BLK
+    lo = torch.tensor(np.asarray(ms["lo"], np.float64), device=dev)
+    hi = torch.tensor(np.asarray(ms["hi"], np.float64), device=dev)
+    ext = (hi - lo) * 0.1
+    lo, hi = (lo - ext).float(), (hi + ext).float()
+    o = torch.empty((max(n, 1), 3), dtype=torch.float32, device=dev)
+    d = torch.empty((max(n, 1), 3), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    for b in range(b0, b1):   # block b of the batch is the same rays whatever the world size
+        g.manual_seed(990000 + b)
+        r = torch.rand((BLK, 5), generator=g, device=dev, dtype=torch.float32)
+        s = slice((b - b0) * BLK, (b - b0 + 1) * BLK)
+        o[s] = lo + r[:, 0:3] * (hi - lo)
+        z = 1.0 - 2.0 * r[:, 3]
+        phi = (2.0 * np.pi) * r[:, 4]
+        rr = torch.sqrt(torch.clamp(1.0 - z * z, min=0.0))
+        d[s, 0] = rr * torch.cos(phi); d[s, 1] = rr * torch.sin(phi); d[s, 2] = z
+    tri = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    tt = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)
+    times, fallback = [], 0
+    for rep in range(5):
+        if n:
+            eng.trace_closest_device(o.data_ptr(), d.data_ptr(), None, n, tri.data_ptr(), tt.data_ptr(), None)
+            st = eng.stats()
+            if rep >= 2:
+                times.append(st["trace_seconds"])
+            fallback = st["fallback_rays"]
+        else:
+            times.append(0.0)
+    secs = float(np.median(times))
+    # 64-bit hash of all ids: sum of id_i * (odd multiplier of the GLOBAL ray index), wrapping
+    idx = torch.arange(b0 * BLK, b0 * BLK + n, device=dev, dtype=torch.int64)
+    hsh = ((tri[:n].to(torch.int64) + 2) * (idx * 2654435761 + 1)).sum() if n else torch.zeros((), dtype=torch.int64, device=dev)
+    hits = (tri[:n] >= 0).sum().to(torch.float64)
+    red = torch.stack([torch.tensor(float(secs), dtype=torch.float64, device=dev), hits, torch.tensor(float(fallback), dtype=torch.float64, device=dev)])
+    if world > 1:
+        mx = red.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = red.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dist.all_reduce(hsh, op=dist.ReduceOp.SUM)
+        secs, hits_total, fallback = float(mx[0]), float(sm[1]), float(sm[2])
+    else:
+        hits_total = float(hits)
+    res = {"what": "BASELINE configs[3]: closest hit, random rays vs the 1M-triangle mesh (geometry only), rays resident in HBM",
+           "triangles": int(len(pos)), "rays": int(nrays), "mrays_per_s": nrays / max(secs, 1e-12) * 1e-6, "ms": secs * 1e3,
+           "hit_fraction": hits_total / nrays, "fallback_rays": int(fallback), "ids_hash64": f"{int(hsh.item()) & 0xFFFFFFFFFFFFFFFF:016x}",
+           "build_ms": build_ms, "timing": "median of 3 after 2 warm-up passes, CUDA events on the engine's stream, max over ranks"}
+    if rank == 0 and n:
+        # fetch counts: instrumented counting build of the same kernel on the same BVH, 1/16 of this rank's rays
+        ce = pt.Engine(device=local_rank, flags=pt.FLAG_COUNT_FETCHES, max_paths=max_paths)
+        ce.upload_scene(pos)
+        m = max(n // 16, 1)
+        tri2 = torch.empty(m, dtype=torch.int32, device=dev); tt2 = torch.empty(m, dtype=torch.float32, device=dev)
+        ce.trace_closest_device(o.data_ptr(), d.data_ptr(), None, m, tri2.data_ptr(), tt2.data_ptr(), None)
+        cs = ce.stats(); info = ce.accel_info(); ce.close()
+        npr, tpr = cs["node_fetches"] / m, cs["tri_fetches"] / m
+        bpr = 32 + 16 + npr * info["wide_node_bytes"] + tpr * info["tri_bytes"]
+        res.update({"nodes_per_ray": npr, "tris_per_ray": tpr, "bytes_per_ray": bpr, "wide_node_bytes": info["wide_node_bytes"],
+                    "achieved_gbs": nrays * bpr / max(secs, 1e-12) * 1e-9, "frac_of_hbm_peak": nrays * bpr / max(secs, 1e-12) * 1e-9 / peak})
+        if ncheck > 0:
+            import oracle
+            step = max(n // ncheck, 1)
+            sel = torch.arange(0, n, step, device=dev)[:ncheck]
+            ho, hd = o[sel].cpu().numpy(), d[sel].cpu().numpy()
+            gt, gtt = tri[sel].cpu().numpy(), tt[sel].cpu().numpy()
+            if oracle.ref_available():
+                orc, kind, cores = oracle.RefOracle(ms["pos"]), "reference", oracle.RefOracle.max_threads()
+                assert np.array_equal(orc.order(), order), "reference BVH order differs from b2pt_reference_order"
+                c0 = time.perf_counter(); rt, rtt = orc.trace_closest(ho, hd); c1 = time.perf_counter()
+            else:
+                orc, kind, cores = oracle.PortOracle(ms["pos"]), "port", oracle.PortOracle.max_threads()
+                c0 = time.perf_counter(); rt, rtt, _ = orc.trace_closest(ho, hd); c1 = time.perf_counter()
+            res.update({"oracle_checked": int(len(sel)), "oracle_kind": kind, "oracle_id_mismatch": int((gt != rt).sum()),
+                        "oracle_t_mismatch": int((gtt.view(np.uint32) != rtt.view(np.uint32)).sum()),
+                        "cpu_mrays_per_s": len(sel) / (c1 - c0) * 1e-6, "cpu_threads": cores})
+    eng.close()
+    del o, d, tri, tt
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -189,14 +336,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--max-paths", type=int, default=32 << 20)
+    ap.add_argument("--no-c4", action="store_true", help="skip the configs[3] closest-hit microbench")
+    ap.add_argument("--c4-rays", type=int, default=100_000_000)
+    ap.add_argument("--c4-check", type=int, default=4_000_000, help="rays of the microbench compared with the reference CPU BVH")
+    ap.add_argument("--max-paths", type=int, default=DEFAULT_MAX_PATHS)
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (reported in config.spp)")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200":
-        args.warmup = max(args.warmup, 0)   # the contract asks for >= 3; honour the flag but it is the caller's call
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -227,11 +375,12 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    W, H, SPP, B, desc = WORKLOADS[args.workload]
+    W, H, SPP, B, _, desc = WORKLOADS[args.workload]
     if args.spp > 0:
         SPP = args.spp
-        desc += f" (spp overridden to {SPP})"
-    sc = make_scene(args.workload)
+    tmp = tempfile.TemporaryDirectory()
+    kind_s, payload = prebuild_arrays(args.workload, tmp.name)
+    sc = make_scene(kind_s, payload)
     cam = pt.Camera()
     eng = pt.Engine(device=local_rank, max_paths=args.max_paths)
     eng.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
@@ -240,14 +389,13 @@ def main():
     if args.scaling == "weak":
         spp_total = SPP * world
         part = D.sample_partition(rank, world, SPP)
-        parallelism = f"sample ranges x{world}, scene replicated, 1 NCCL reduce/frame" if world > 1 else "single GPU"
     else:
         spp_total = SPP
         part = D.tile_partition(rank, world, 32)
-        parallelism = f"interleaved 1024-pixel tiles x{world}, scene replicated, 1 NCCL reduce/frame" if world > 1 else "single GPU"
 
     d_rgb = torch.empty(W * H * 3, dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    h_rgb = torch.empty(W * H * 3, dtype=torch.float32, pin_memory=True) if rank == 0 else None
 
     def step_device():
         flush.zero_()                      # L2 flush between iterations (on torch's stream; synchronised below)
@@ -276,6 +424,11 @@ def main():
     barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop() if rank == 0 else None
+    # the combined frame (rank 0): 64-bit hash of its bytes — identical for every N under the tile partition
+    frame_hash = None
+    if rank == 0:
+        h_rgb.copy_(d_rgb); torch.cuda.synchronize(dev)
+        frame_hash = hashlib.blake2b(h_rgb.numpy().tobytes(), digest_size=8).hexdigest()
 
     wall = t1 - t0
     vals = torch.tensor([wall, agg["gpu_seconds"], float(agg["samples"]), float(agg["extend_rays"] + agg["shadow_rays"]),
@@ -299,15 +452,17 @@ def main():
     r.uploadScene(sc); r.render(cam, part)   # warm-up (allocations)
     barrier()
     e0 = time.perf_counter()
-    e_steps = max(1, min(args.steps, 2))
+    e_steps = max(1, args.steps)
     for _ in range(e_steps):
         r.uploadScene(sc)                       # host scene -> device (H2D inside the timed region)
         if world == 1:
             fb = r.render(cam, part)            # device -> host framebuffer (D2H inside the timed region)
         else:
-            # each rank renders its share on the device, ONE NCCL sum-reduce, rank 0 copies the frame to the host
+            # each rank renders its share on the device, ONE NCCL sum-reduce, rank 0 copies the frame into pinned host memory
             D.render_distributed(r.engine, cam.c, W, H, spp_total, B, d_rgb, part, seed=1234)
-            fb = d_rgb.cpu().numpy() if rank == 0 else None
+            if rank == 0:
+                h_rgb.copy_(d_rgb, non_blocking=True)
+                torch.cuda.synchronize(dev)
     barrier()
     e1 = time.perf_counter()
     e_wall = e1 - e0
@@ -320,13 +475,22 @@ def main():
     d2h = int(W * H * 3 * 4)
     r.engine.close()
 
+    peak, peak_src = load_peaks()
+
+    # ---- configs[3] in the same run (every rank traces its shard of the batch) --------------------------------
+    c4 = None
+    if not args.no_c4:
+        eng.close()   # free the render engine's wavefront buffers first
+        eng = None
+        torch.cuda.empty_cache()
+        c4 = c4_microbench(pt, torch, dist, dev, local_rank, rank, world, args.c4_rays, args.c4_check, peak, args.max_paths)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (measured live with CUDA events on the engine's stream) --------
-    peak, peak_src = load_peaks()
     ce = pt.Engine(device=local_rank, flags=pt.FLAG_COUNT_FETCHES, max_paths=args.max_paths)
     ce.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
     ce.render(cam.c, W // 4, H // 4, 4, B, seed=1234)      # instrumented counting build of the same kernels
@@ -347,54 +511,66 @@ def main():
         k_rays, k_secs, k_launches, io = agg["extend_rays"], agg["extend_seconds"], agg["extend_launches"], 32 + 16
     bytes_per_ray = io + nodes_per_ray * info["wide_node_bytes"] + tris_per_ray * info["tri_bytes"]
     achieved = k_rays * bytes_per_ray / max(k_secs, 1e-12) * 1e-9
-    traffic, traffic_src, issue = None, None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and args.max_paths == (32 << 20) and args.spp == 0:   # captured at this batch size
-        tj = json.load(open(tpath)).get(args.workload, {}).get(dominant)
-        if tj:
+    frac = achieved / peak
+    ms_per_launch = 1e3 * k_secs / max(k_launches, 1)
+    traffic = traffic_src = issue = frac_hbm_measured = None
+    bound = "hbm" if frac <= 1.0 else "issue"
+    src_hash = kernel_source_hash()
+    capture_note = "no ncu capture committed for this workload/kernel"
+    if os.path.exists(TRAFFIC_JSON) and args.max_paths == DEFAULT_MAX_PATHS and args.spp == 0:
+        tj_all = json.load(open(TRAFFIC_JSON))
+        tj = tj_all.get(args.workload, {}).get(dominant)
+        if tj and tj_all.get("source_hash") == src_hash:
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            frac_hbm_measured = traffic / (ms_per_launch * 1e-3) * 1e-9 / peak
             # what actually bounds the kernel: warp-instruction issue (4 schedulers x 148 SMs x SM clock)
-            issue = {"warp_instructions_per_launch": tj["warp_instructions_per_launch"], "issue_active_pct_ncu": tj["issue_active_pct"],
-                     "active_lanes_per_instruction_ncu": tj["active_lanes_per_instruction"],
-                     "achieved_gwarp_inst_per_s": tj["warp_instructions_per_launch"] / max(k_secs / max(k_launches, 1), 1e-12) * 1e-9,
+            issue = {"issue_active_pct_ncu": tj["issue_active_pct"], "active_lanes_per_instruction_ncu": tj["active_lanes_per_instruction"],
+                     "warp_instructions_per_launch_ncu": tj["warp_instructions_per_launch"],
                      "peak_gwarp_inst_per_s": 148 * 4 * 1.965}
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "issue": issue, "algorithmic_bytes_per_launch": k_rays * bytes_per_ray / max(k_launches, 1),
+            bound = tj.get("bound", bound)
+            capture_note = f"ncu capture of the same kernel sources ({src_hash})"
+        elif tj:
+            capture_note = f"ncu capture is from other kernel sources ({tj_all.get('source_hash')} != {src_hash}): not quoted"
+    roofline = {"bound": bound, "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac,
+                "traffic": traffic, "traffic_source": traffic_src, "frac_hbm_measured": frac_hbm_measured, "issue": issue,
+                "algorithmic_bytes_per_launch": k_rays * bytes_per_ray / max(k_launches, 1),
                 "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
-                "tris_per_ray": tris_per_ray, "kernel_ms_per_launch": 1e3 * k_secs / max(k_launches, 1), "kernel_launches": k_launches,
-                "kernel_share_of_step": k_secs / max(dev_s, 1e-12),
-                "note": "algorithmic bytes (SURVEY 8d) = per-ray queue I/O + mean wide-node fetches x 224 B + mean triangle fetches x 48 B, "
-                        "fetch counts from the counting build of the same kernels on a 1/16-size frame. frac > 1 means the node/triangle "
-                        "fetches are served by L1/L2, not HBM (the whole BVH of this workload is cache resident; compare `traffic`, the "
-                        "DRAM bytes ncu measured per launch): the kernel is then bound by instruction issue, not by the memory roofline "
-                        "(ncu: profiles/r01_ncu_c2_batch_v10.txt, issue slots 82 % busy; see `issue`)"}
+                "tris_per_ray": tris_per_ray, "wide_node_bytes": info["wide_node_bytes"],
+                "kernel_ms_per_launch": ms_per_launch, "kernel_launches": k_launches,
+                "kernel_share_of_step": k_secs / max(dev_s, 1e-12), "kernel_source_hash": src_hash, "capture": capture_note,
+                "note": "algorithmic bytes (SURVEY 8d) = per-ray queue I/O + mean wide-node fetches x node bytes + mean triangle fetches x 48 B, "
+                        "fetch counts from the counting build of the same kernels on a 1/16-size frame.  The BVH of a 1M-triangle scene "
+                        "(~100 MB) is L2-resident, so these fetches are mostly served by L1/L2: `frac` is the algorithmic traffic against "
+                        "the HBM peak, `frac_hbm_measured` the DRAM bytes ncu counted per launch against the same peak, and `bound` what "
+                        "limits the kernel (issue = warp-instruction issue slots, see `issue`)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        secs0, ns0, kind, cores, _ = cpu_render(sc, W, H, 1, B, args.workload,
-                                                (W // 2 - 120, H // 2 - 68, W // 2 + 120, H // 2 + 68) if args.workload in ("c3", "c5") else None)
-        spp_c = max(1, min(SPP, int(15.0 / max(secs0, 1e-3))))
-        window = (W // 2 - 120, H // 2 - 68, W // 2 + 120, H // 2 + 68) if args.workload in ("c3", "c5") else None
-        secs, ns, kind, cores, _ = cpu_render(sc, W, H, spp_c, B, args.workload, window)
+        orc, kind, cores = make_cpu_oracle(kind_s, payload)
+        secs0, _ = cpu_render(orc, kind, W, H, 1, B)
+        spp_c = max(1, min(SPP, int(12.0 / max(secs0, 1e-3))))
+        secs, ns = cpu_render(orc, kind, W, H, spp_c, B)
         cpu_baseline = {"value": ns / secs * 1e-6, "unit": "Msamples/s", "cores": cores, "kind": kind,
-                        "sample": f"{W}x{H}" + (f" crop {window}" if window else "") + f", {spp_c} of {SPP} spp, {B} bounces ({ns} samples, {secs:.1f} s)"}
+                        "sample": cpu_sample_text(W, H, spp_c, SPP, B, cores, kind) + f" ({ns} samples, {secs:.1f} s)"}
 
     line = {
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": desc, "width": W, "height": H, "spp": spp_total, "bounces": B, "triangles": int(len(sc.pos)),
-                   "parallelism": parallelism, "max_paths_in_flight": args.max_paths,
-                   "l2": "256 MB buffer written between timed iterations (L2 flush); per-batch path state (GBs) also exceeds L2"},
+        "config": config_dict(args, world, len(sc.pos)),
         "mrays_per_s": rays / wall * 1e-6, "rays_per_sample": rays / samples, "device_ms_per_step": 1e3 * dev_s / args.steps,
         "extend_ms_per_step": 1e3 * agg["extend_seconds"] / args.steps, "shadow_ms_per_step": 1e3 * agg["shadow_seconds"] / args.steps,
+        "extend_mrays_per_s": agg["extend_rays"] / max(agg["extend_seconds"], 1e-12) * 1e-6,
+        "shadow_mrays_per_s": agg["shadow_rays"] / max(agg["shadow_seconds"], 1e-12) * 1e-6,
         "fallback_rays_per_step": agg["fallback_rays"] / args.steps, "build_ms": 1e3 * build_s,
-        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "frame_hash": frame_hash,
+        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
                 "what": "B200Renderer.uploadScene + render with host buffers (the region src/main.cpp:87-92 times)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "c4": c4,
     }
     emit(line)
     if world > 1:
