@@ -89,7 +89,7 @@ typedef struct b2pt_config {
 
 #define B2PT_FLAG_COUNT_FETCHES 1  /* instrumented traversal: count node / triangle fetches (slower) */
 #define B2PT_FLAG_EXACT_ONLY 2     /* closest-hit queries use only the exact reference-order DFS kernel */
-#define B2PT_FLAG_OCTET 4          /* batch queries use the 8-lanes-per-ray cooperative kernels instead of one ray per lane */
+#define B2PT_FLAG_NO_LEARN_ORDER 8 /* do not re-order wide-node children by measured occlusion rate after the first batch */
 
 /* Counters of the last trace / render call. */
 typedef struct b2pt_stats {
@@ -167,9 +167,10 @@ int b2pt_tonemap(b2pt_ctx* ctx, const float* d_rgb, int64_t n_pixels, float gamm
 
 /* ---- introspection ------------------------------------------------------------------------------ */
 int b2pt_get_stats(const b2pt_ctx* ctx, b2pt_stats* out);
-/* Sizes of the acceleration structure built by the last upload: out[0]=wide nodes, out[1]=bytes per
- * wide node, out[2]=reference leaves, out[3]=reference binary nodes, out[4]=triangle bytes. */
-int b2pt_get_accel_info(const b2pt_ctx* ctx, int64_t* out5);
+/* The acceleration structure built by the last upload: out[0]=wide nodes, out[1]=bytes per wide node,
+ * out[2]=reference leaves, out[3]=reference binary nodes, out[4]=triangle bytes, out[5]=clustering (PLOC)
+ * iterations run as separate launches, out[6]=levels of the wide tree, out[7]=reference leaves hoisted out of the tree (tested by every ray). */
+int b2pt_get_accel_info(const b2pt_ctx* ctx, int64_t* out8);
 /* The CUDA stream all of the context's kernels are launched on (cudaStream_t as void*). */
 void* b2pt_stream(const b2pt_ctx* ctx);
 /* Library version string. */

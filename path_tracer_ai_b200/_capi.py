@@ -11,12 +11,12 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2pt.so")
+LIB_PATH = os.environ.get("B2PT_LIB") or os.path.join(_HERE, "libb2pt.so")   # B2PT_LIB: an experiment build of the same library
 
 DIFFUSE, SPECULAR, DIELECTRIC = 0, 1, 2
 FLAG_COUNT_FETCHES = 1
 FLAG_EXACT_ONLY = 2
-FLAG_OCTET = 4
+FLAG_NO_LEARN_ORDER = 8
 
 
 class Material(C.Structure):
@@ -270,10 +270,10 @@ class Engine:
         return s.as_dict()
 
     def accel_info(self) -> dict:
-        out = np.zeros(5, np.int64)
+        out = np.zeros(8, np.int64)
         self._check(self._L.b2pt_get_accel_info(self._h, _p(out)), "b2pt_get_accel_info")
         return dict(wide_nodes=int(out[0]), wide_node_bytes=int(out[1]), ref_leaves=int(out[2]), ref_nodes=int(out[3]),
-                    tri_bytes=int(out[4]))
+                    tri_bytes=int(out[4]), ploc_iterations=int(out[5]), wide_levels=int(out[6]), hoisted_leaves=int(out[7]))
 
     @property
     def stream(self) -> int:

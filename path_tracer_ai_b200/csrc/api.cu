@@ -1,6 +1,7 @@
 // api.cu — the C ABI declared in include/b2pt.h.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -96,11 +97,13 @@ int b2pt_create(const b2pt_config* cfg, b2pt_ctx** out) {
     b2pt_ctx* ctx = new b2pt_ctx();
     ctx->device = dev;
     ctx->flags = cfg ? cfg->flags : 0;
+    ctx->learn_order = (ctx->flags & B2PT_FLAG_NO_LEARN_ORDER) == 0;
+    ctx->debug_sync = std::getenv("B2PT_DEBUG_SYNC") != nullptr;   // read once, here
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_paths = (cfg && cfg->max_paths_in_flight > 0) ? cfg->max_paths_in_flight : (int64_t)(16 << 20);   // larger wavefronts amortise the kernels' tails: 1M-triangle render 150 (2M) / 185 (8M) / 194 (16M) Msamples/s
     auto fail = [&](cudaError_t err, const char* what) {
         cuda_fail(nullptr, err, what, __FILE__, __LINE__);
-        delete ctx;
+        b2pt_destroy(ctx);   // releases whatever was created so far
         return B2PT_ERR_CUDA;
     };
     if ((e = cudaSetDevice(dev)) != cudaSuccess) return fail(e, "cudaSetDevice");
@@ -127,6 +130,7 @@ void b2pt_destroy(b2pt_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -297,9 +301,9 @@ int b2pt_get_stats(const b2pt_ctx* ctx, b2pt_stats* out) {
     return B2PT_OK;
 }
 
-int b2pt_get_accel_info(const b2pt_ctx* ctx, int64_t* out5) {
-    if (!ctx || !out5) return B2PT_ERR_INVALID;
-    std::memcpy(out5, ctx->accel_info, sizeof(ctx->accel_info));
+int b2pt_get_accel_info(const b2pt_ctx* ctx, int64_t* out8) {
+    if (!ctx || !out8) return B2PT_ERR_INVALID;
+    std::memcpy(out8, ctx->accel_info, sizeof(ctx->accel_info));
     return B2PT_OK;
 }
 

@@ -23,18 +23,14 @@ namespace b2pt {
 //   node_info[i] = (start, end, right child index or -1 for leaves, leaf id or -1)
 //   leaf_lo/leaf_hi[l]    = the same boxes, indexed by leaf id (what visibility is defined on)
 //
-// Wide BVH (8-ary collapse of the reference tree; full-precision child boxes, SoA inside the node):
+// Traversal tree (8-wide BVH over the reference LEAVES, built on the device: build.cu; full-precision child
+// boxes, SoA inside the node so that a lane reads four children's planes with one 16-byte load):
 struct __align__(32) WideNode {
     float lox[8], loy[8], loz[8];
     float hix[8], hiy[8], hiz[8];
     uint32_t child[8];   // 0xFFFFFFFF empty | leaf: bit31, count-1 in [30:28], first tri in [27:0] | inner: node index
 };
 static_assert(sizeof(WideNode) == 224, "WideNode layout");
-
-// Deepest inner wide node (root = level 0) a scene may have: the run-to-completion kernels keep at most 7 pending
-// siblings per level plus the 8 children of the node being expanded on an unchecked stack (traverse_rtc.cuh);
-// build_scene refuses deeper trees (2^28 triangles need 9-10 levels).
-#define B2PT_MAX_WIDE_LEVEL 12
 
 #define B2PT_CHILD_EMPTY 0xFFFFFFFFu
 #define B2PT_CHILD_LEAF 0x80000000u
@@ -43,6 +39,10 @@ struct DMaterial { int type; float r, g, b, roughness, metallic, ior, pad; };
 struct DLight { float px, py, pz, cr, cg, cb, intensity, pad; };
 
 #define B2PT_MAX_LIGHTS 16
+// Reference leaves whose box covers most of the scene (the loader's 16-unit room triangles, src/scene.cpp:118-209, sit
+// in one or two of them) are kept OUT of the traversal tree: every ray would visit them anyway, so each ray tests
+// them once, up front, while the lanes of its warp are still in lock-step (traverse_rtc.cuh).
+#define B2PT_MAX_HOIST 4
 
 struct DeviceScene {
     int ntri;
@@ -60,6 +60,10 @@ struct DeviceScene {
     const DMaterial* mats;
     int nmat;
     int nlight;
+    float coord_bound;   // largest |coordinate| in the scene (absolute part of the distance-cull slack, traverse.cuh)
+    int nhoist;                              // reference leaves tested by every ray before the traversal
+    int hoist_leaf[B2PT_MAX_HOIST];          // their leaf ids ...
+    uint32_t hoist_code[B2PT_MAX_HOIST];     // ... and child codes (first triangle, count)
     DLight lights[B2PT_MAX_LIGHTS];
 };
 
@@ -71,7 +75,7 @@ struct TraceCounters { unsigned long long fallback, node_fetches, tri_fetches, p
 }  // namespace b2pt
 
 // ---- host context -----------------------------------------------------------------------------------
-#define B2PT_SCRATCH_SLOTS 32   // 0..15: per-call scratch (trace / render), 16..31: scene buffers and upload staging
+#define B2PT_SCRATCH_SLOTS 64   // 0..15: per-call scratch (trace / render), 16..: scene buffers, upload staging, build scratch
 struct b2pt_ctx {
     int device = 0;
     int flags = 0;
@@ -79,31 +83,31 @@ struct b2pt_ctx {
     int64_t max_paths = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;    // per-bounce timing events of render_frame, created once and reused
+    bool debug_sync = false;             // B2PT_DEBUG_SYNC=1 at b2pt_create: synchronise after every render kernel
     std::string err;
     bool has_scene = false;
     // occluder-aware child order (build.cu learn_child_order): 0 = collect statistics during the next wavefront
     // batch, 1 = collected (re-order before the next batch), 2 = done / off
     int order_state = 2;
+    bool learn_order = true;             // cleared by B2PT_FLAG_NO_LEARN_ORDER
     unsigned* d_order_stats = nullptr;   // visits[nwide*8] then hits[nwide*8]
     b2pt::DeviceScene scene{};
-    // owned device allocations of the scene
-    std::vector<void*> scene_allocs;
     // scratch (grown on demand)
     void* scratch[B2PT_SCRATCH_SLOTS] = {};
     size_t scratch_bytes[B2PT_SCRATCH_SLOTS] = {};
-    // host topology of the reference tree + collapse, cached by triangle count (build.cu)
+    // host topology of the reference tree, cached by triangle count (build.cu)
     struct Topology {
         bool valid = false, on_device = false;
-        int ntri = -1, nnodes = 0, nleaves = 0, maxdepth = 0, max_wide_level = 0;
+        int ntri = -1, nnodes = 0, nleaves = 0, maxdepth = 0;
         std::vector<int4> info;
-        std::vector<int> wide_src, ids_flat;
-        std::vector<uint32_t> wide_child;
+        std::vector<int> ids_flat;
         std::vector<std::pair<size_t, size_t>> spans;
     } topo;
     b2pt::TraceCounters* d_counters = nullptr;
     int* d_fallback_count = nullptr;
     b2pt_stats stats{};
-    int64_t accel_info[5] = {};
+    int64_t accel_info[8] = {};
 };
 
 namespace b2pt {

@@ -5,12 +5,12 @@
 // One frame = pixel chunks x sample chunks of at most `max_paths` camera paths.  Per chunk:
 //   k_raygen                         camera rays (camera.hpp:18-29), T = 1, L = 0
 //   for depth in 0 .. maxBounces-1:
-//     k_extend (+ k_extend_fallback)  closest hit: one ray per lane, persistent warps with lane refill
+//     k_extend_rtc (+ k_extend_fallback)  closest hit, one ray per thread; uncertified rays -> exact recursion
 //     k_hitinfo                       hit point, shading normal, material; bins the path into its material
 //                                     queue (1-pass counting sort on the material type) and into the
-//                                     direct-light queue
-//     k_shadow                        one ray per (vertex, light): any-hit traversal -> visibility byte
-//     k_shade<DIFFUSE|SPECULAR|DIELECTRIC>  direct light from the visible lights (summed in light order),
+//                                     direct-light queue (fused into k_extend_rtc on small trees)
+//     k_shadow_rtc                    one ray per (vertex, light): any-hit traversal -> visibility byte
+//     k_shade                         direct light from the visible lights (summed in light order),
 //                                     L += T*direct, BSDF sample, T update, next ray -> next queue
 //   k_resolve                        per pixel: samples added in sample order (renderer.hpp:69-72)
 // k_finalize divides by spp (renderer.hpp:75-81).
@@ -25,7 +25,6 @@
 #include <cstdlib>
 
 #include "traverse_rtc.cuh"
-#include "traverse_thread.cuh"
 
 namespace b2pt {
 
@@ -224,56 +223,8 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
 #ifndef B2PT_EXT_MINB
 #define B2PT_EXT_MINB 10
 #endif
-#define B2PT_WF_CHUNK 256   // queue entries a warp claims per global atomic
-#define B2PT_WF_REFILL 4    // idle lanes that trigger a refill
-
-// Closest hit for the active paths: one ray per lane, persistent warps that refill idle lanes from a
-// warp-local pool of queue entries.  Writes the hit record; uncertified rays go to the fallback queue.
-template <bool COUNT, int TPS>
-__global__ void __launch_bounds__(B2PT_TBLOCK) k_extend(int refill_min, DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
-                                                        int P, TraceCounters* __restrict__ tc) {
-    __shared__ uint2 lane_stacks[B2PT_SSTACK * B2PT_TBLOCK];
-    LaneState st;
-    st.stack.sm = lane_stacks + threadIdx.x;
-    WarpPool pool{0, 0, false};
-    const long long total = list ? *count_ptr : P;
-    int p = -1;
-    unsigned n_nodes = 0, n_tris = 0;
-    while (true) {
-        unsigned idle = __ballot_sync(0xffffffffu, p < 0);
-        if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
-            long long got = warp_pool_take<B2PT_WF_CHUNK>(pool, &W.totals[4], total, p < 0);
-            if (p < 0 && got >= 0) {
-                p = list ? list[got] : (int)got;
-                float4 o4 = W.ro[p], d4 = W.rd[p];
-                RayQ r;
-                r.o = f4v(o4); r.d = f4v(d4);
-                r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
-                r.T0 = B2PT_INF;
-                lane_begin(st, r);
-                if (S.nwide == 0) { W.hit[p] = make_float4(B2PT_INF, __int_as_float(-1), 0.0f, 0.0f); p = -1; }
-            }
-            if (__ballot_sync(0xffffffffu, p >= 0) == 0 && pool.exhausted) break;
-        }
-        if (p >= 0) {
-            if (lane_closest_step<COUNT, TPS>(S, st, n_nodes, n_tris)) {
-                W.hit[p] = make_float4(st.best.t, __int_as_float(st.best.tri), st.best.u, st.best.v);
-                if (!lane_certify(S, st)) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
-                p = -1;
-            }
-        }
-    }
-    if (COUNT) {
-        for (int off = 16; off > 0; off >>= 1) {
-            n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
-            n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
-        }
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
-    }
-}
-
-// Run-to-completion variants for coherent batches (traverse_rtc.cuh): one thread per queue entry.
-// The closest-hit kernel also runs the per-vertex epilogue of its certified rays (hit point, shading normal,
+// Closest hit for the active paths (traverse_rtc.cuh): one thread per queue entry.
+// With FUSED the kernel also runs the per-vertex epilogue of its certified rays (hit point, shading normal,
 // material, light culling, binning — hit_epilogue + bin_path): the hit record never goes through HBM and the
 // bandwidth-bound epilogue overlaps other warps' traversal.  Uncertified rays get theirs in k_extend_fallback.
 // FUSED = false: the hit record is written and k_hitinfo does the rest.  Measured: fusing wins on scenes whose
@@ -292,10 +243,7 @@ __global__ void __launch_bounds__(FUSED ? B2PT_EXT_BLOCK_FUSED : B2PT_EXT_BLOCK,
     if (k < total) {
         p = list ? list[k] : k;
         float4 o4 = W.ro[p], d4 = W.rd[p];
-        RayQ r;
-        r.o = f4v(o4); r.d = f4v(d4);
-        r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
-        r.T0 = B2PT_INF;
+        RayQ r = make_rayq_normalised(f4v(o4), f4v(d4), B2PT_INF);
         HitRec h;
         bool ok = closest_rtc<COUNT>(S, r, h, n_nodes, n_tris);
         if (!FUSED) W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
@@ -366,10 +314,7 @@ __global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) 
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         int p = W.q_fallback[k];
         float4 o4 = W.ro[p], d4 = W.rd[p];
-        RayQ r;
-        r.o = f4v(o4); r.d = f4v(d4);
-        r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
-        r.T0 = B2PT_INF;
+        RayQ r = make_rayq_normalised(f4v(o4), f4v(d4), B2PT_INF);
         HitRec h;
         closest_exact_dfs(S, r, h);
         if (!FUSED) {
@@ -419,59 +364,6 @@ __device__ __forceinline__ float schlick_fresnel(float cosTheta, float F0) {
     float x2 = B2PT_MUL(x, x);
     float x5 = B2PT_MUL(B2PT_MUL(x2, x2), x);
     return B2PT_ADD(F0, B2PT_MUL(B2PT_SUB(1.0f, F0), x5));
-}
-
-// Shadow rays of calculateDirectLighting (renderer.hpp:271-278): one work item per (vertex, light), one ray per
-// lane, persistent warps with refill.  Writes vis[p * nlight + l] = 1 when Scene::intersect would return true.
-template <bool COUNT, int TPS>
-__global__ void __launch_bounds__(B2PT_TBLOCK) k_shadow(int refill_min, DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
-    __shared__ uint2 lane_stacks[B2PT_SSTACK * B2PT_TBLOCK];
-    LaneState st;
-    st.stack.sm = lane_stacks + threadIdx.x;
-    WarpPool pool{0, 0, false};
-    const int nl = S.nlight;
-    const long long total = W.counters[C_SHADOW];
-    long long slot = -1;   // index into vis of the ray this lane is tracing
-    unsigned n_nodes = 0, n_tris = 0;
-    while (true) {
-        unsigned idle = __ballot_sync(0xffffffffu, slot < 0);
-        if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
-            long long got = warp_pool_take<B2PT_WF_CHUNK>(pool, &W.totals[5], total, slot < 0);
-            if (slot < 0 && got >= 0) {
-                int e = W.q_shadow[got];
-                int p = e / nl, l = e - p * nl;
-                float4 g0 = W.g0[p], g1 = W.g1[p];
-                V3 P = f4v(g0), n = f4v(g1);
-                const DLight& lt = S.lights[l];
-                V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
-                float dist = vlength(lightDir);
-                slot = e;
-                if (S.nwide == 0) {       // empty scene
-                    W.vis[slot] = 0;
-                    slot = -1;
-                } else {
-                    lightDir = vnormalize(lightDir);
-                    lane_begin(st, make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f)));   // :274-275
-                }
-            }
-            if (__ballot_sync(0xffffffffu, slot >= 0) == 0 && pool.exhausted) break;
-        }
-        if (slot >= 0) {
-            int res = lane_any_step<COUNT, TPS>(S, st, n_nodes, n_tris);
-            if (res) {
-                if (res == 3) { HitRec h; closest_exact_dfs(S, st.r, h); res = h.tri >= 0 ? 1 : 2; }
-                W.vis[slot] = res == 1 ? 1 : 0;
-                slot = -1;
-            }
-        }
-    }
-    if (COUNT) {
-        for (int off = 16; off > 0; off >>= 1) {
-            n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
-            n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
-        }
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
-    }
 }
 
 // calculateDirectLighting (renderer.hpp:252-301) given the visibility of every light.
@@ -748,28 +640,23 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     B2PT_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(float4) * (size_t)nown, stream));
 
     const bool count = (ctx->flags & B2PT_FLAG_COUNT_FETCHES) != 0;
-    const int tu_refill = std::getenv("B2PT_WF_REFILL") ? std::atoi(std::getenv("B2PT_WF_REFILL")) : 4;
-    const int tu_tps = std::getenv("B2PT_WF_TPS") ? std::atoi(std::getenv("B2PT_WF_TPS")) : 4;
-    // B2PT_WF_MODE: 1 = run-to-completion kernels for every bounce (default), 2 = persistent kernels for every
-    // bounce, 0 = run-to-completion for depth 0 and small scenes, persistent otherwise.  Measured (profiles/
-    // r01_render_modes.txt): queue neighbours are neighbouring pixels, so even bounce rays start from nearby
-    // points and mode 1 wins in every rendered scene tried; the persistent kernels win only on unordered ray
-    // batches (b2pt_trace_*: 2.1 vs 1.0 Grays/s on random rays in 1M triangles).
-    const int force_mode = std::getenv("B2PT_WF_MODE") ? std::atoi(std::getenv("B2PT_WF_MODE")) : 1;
-    // closest-hit kernel with the per-vertex epilogue fused in: small trees only (see k_extend_rtc); B2PT_FUSE=0/1 forces
-    const bool fused = std::getenv("B2PT_FUSE") ? std::atoi(std::getenv("B2PT_FUSE")) != 0 : S.nwide <= 64;
-    const int coherent_nodes = std::getenv("B2PT_COHERENT_NODES") ? std::atoi(std::getenv("B2PT_COHERENT_NODES")) : 512;
+    // closest-hit kernel with the per-vertex epilogue fused in: small trees only (see k_extend_rtc)
+    const bool fused = S.nwide <= 64;
     int64_t launches = 0, n_extend = 0, n_shadow = 0;
     float extend_ms = 0.0f, shadow_ms = 0.0f;
-    // Traversal time is measured with events around extend+direct of every bounce; to avoid a sync
-    // per bounce the events are created once per call and read at the end.
-    std::vector<cudaEvent_t> evs;
-    auto ev = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); evs.push_back(e); };
+    // Traversal time is measured with events around extend + direct of every bounce; they come from a pool owned by
+    // the context (created once, reused by every frame) and are read after the frame's single synchronisation.
+    size_t ev_used = 0;
+    auto ev = [&]() {
+        if (ev_used == ctx->ev_pool.size()) { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) return; ctx->ev_pool.push_back(e); }
+        cudaEventRecord(ctx->ev_pool[ev_used++], stream);
+    };
 
     // B2PT_DEBUG_SYNC=1: synchronise after every kernel and name the first one that faults (debugging aid).
-    const bool dbg_sync = std::getenv("B2PT_DEBUG_SYNC") != nullptr;
+    const bool dbg_sync = ctx->debug_sync;
     std::string dbg_fault;
     auto dbg = [&](const char* kernel, long long pb, int sb_, int depth_) {
+        ++launches;
         if (!dbg_sync || !dbg_fault.empty()) return;
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e == cudaSuccess) e = cudaGetLastError();
@@ -789,32 +676,22 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
             int P = npc * ns;
             int sabs = s_begin + sb;
             k_raygen<<<(P + 255) / 256, 256, 0, stream>>>(Wv, C, F, pix_begin, npc, sabs, P);
-            ++launches;
             dbg("k_raygen", pix_begin, sb, -1);
             for (int depth = 0; depth < st->max_bounces; ++depth) {
                 int cur = depth & 1;
                 k_begin_bounce<<<1, 1, 0, stream>>>(Wv, cur, depth == 0, P, S.nlight);
+                dbg("k_begin_bounce", pix_begin, sb, depth);
                 const int* list = depth == 0 ? nullptr : Wv.q_active[cur];
                 ev();
-                // Coherent batches (camera rays and their shadow rays; any ray of a tiny scene) take the
-                // run-to-completion kernels, incoherent ones the persistent kernels with lane refill.
-                const bool coherent = force_mode == 1 || (force_mode == 0 && (depth == 0 || S.nwide <= coherent_nodes));
-                if (coherent) {
-                    if (fused) {
-                        if (count) k_extend_rtc<true, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                        else k_extend_rtc<false, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    } else {
-                        if (count) k_extend_rtc<true, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                        else k_extend_rtc<false, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    }
+                if (fused) {
+                    if (count) k_extend_rtc<true, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else k_extend_rtc<false, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 } else {
-                    unsigned egrid = (unsigned)std::min<long long>(((long long)P + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (long long)ctx->sm_count * 12);
-                    if (count) k_extend<true, 4><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    else if (tu_tps == 8) k_extend<false, 8><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    else k_extend<false, 4><<<egrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    if (count) k_extend_rtc<true, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else k_extend_rtc<false, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 }
-                dbg("k_extend", pix_begin, sb, depth);
-                if (coherent && fused) {   // k_extend_rtc has already run the epilogue of its certified rays
+                dbg("k_extend_rtc", pix_begin, sb, depth);
+                if (fused) {   // k_extend_rtc has already run the epilogue of its certified rays
                     k_extend_fallback<true><<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
                     dbg("k_extend_fallback", pix_begin, sb, depth);
                 } else {
@@ -822,38 +699,26 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                     dbg("k_extend_fallback", pix_begin, sb, depth);
                     k_hitinfo<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
                     dbg("k_hitinfo", pix_begin, sb, depth);
-                    ++launches;
                 }
                 k_after_extend<<<1, 1, 0, stream>>>(Wv, S.nlight);
+                dbg("k_after_extend", pix_begin, sb, depth);
                 ev();
                 ++n_extend;
                 if (S.nlight > 0) {
                     ++n_shadow;
-                    if (learn_batch) {
-                        unsigned sg = (unsigned)(((long long)P * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
-                        k_shadow_learn<<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_order_stats, ctx->d_order_stats + 8 * (size_t)S.nwide);
-                    } else if (coherent) {
-                        unsigned sg = (unsigned)(((long long)P * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
-                        if (count) k_shadow_rtc<true><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
-                        else k_shadow_rtc<false><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
-                    } else {
-                        unsigned sgrid = (unsigned)std::min<long long>(((long long)P * S.nlight + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (long long)ctx->sm_count * 12);
-                        if (count) k_shadow<true, 4><<<sgrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, ctx->d_counters);
-                        else if (tu_tps == 8) k_shadow<false, 8><<<sgrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, ctx->d_counters);
-                        else k_shadow<false, 4><<<sgrid, B2PT_TBLOCK, 0, stream>>>(tu_refill, S, Wv, ctx->d_counters);
-                    }
-                    ++launches;
+                    unsigned sg = (unsigned)(((long long)P * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
+                    if (learn_batch) k_shadow_learn<<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_order_stats, ctx->d_order_stats + 8 * (size_t)S.nwide);
+                    else if (count) k_shadow_rtc<true><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
+                    else k_shadow_rtc<false><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
+                    dbg("k_shadow_rtc", pix_begin, sb, depth);
                 }
                 ev();
-                dbg("k_shadow", pix_begin, sb, depth);
                 int nxt = cur ^ 1;
                 k_shade<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
-                launches += 5;
                 dbg("k_shade", pix_begin, sb, depth);
             }
             if (learn_batch) ctx->order_state = 1;
             k_resolve<<<(npc + 255) / 256, 256, 0, stream>>>(Wv, (float4*)accum, pix_begin, npc, ns);
-            ++launches;
             dbg("k_resolve", pix_begin, sb, -1);
         }
     }
@@ -863,13 +728,12 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     unsigned long long totals[3] = {0, 0, 0};
     cudaError_t ce = cudaMemcpyAsync(totals, Wv.totals, sizeof(totals), cudaMemcpyDeviceToHost, stream);
     cudaError_t se = cudaStreamSynchronize(stream);
-    for (size_t i = 0; i + 2 < evs.size(); i += 3) {   // per bounce: before extend, after extend, after direct
+    for (size_t i = 0; i + 2 < ev_used; i += 3) {   // per bounce: before extend, after extend, after direct
         float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, evs[i], evs[i + 1]) == cudaSuccess) extend_ms += ms;
-        if (cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]) == cudaSuccess) shadow_ms += ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) extend_ms += ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i + 1], ctx->ev_pool[i + 2]) == cudaSuccess) shadow_ms += ms;
     }
-    for (cudaEvent_t e : evs) cudaEventDestroy(e);
-    if (!dbg_fault.empty()) { ctx->err = "render kernel fault: " + dbg_fault; for (cudaEvent_t e : evs) cudaEventDestroy(e); return B2PT_ERR_CUDA; }
+    if (!dbg_fault.empty()) { ctx->err = "render kernel fault: " + dbg_fault; return B2PT_ERR_CUDA; }
     if (le != cudaSuccess) { cuda_fail(ctx, le, "render kernels", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
     if (ce != cudaSuccess) { cuda_fail(ctx, ce, "cudaMemcpyAsync(totals)", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
     if (se != cudaSuccess) { cuda_fail(ctx, se, "cudaStreamSynchronize", __FILE__, __LINE__); return B2PT_ERR_CUDA; }

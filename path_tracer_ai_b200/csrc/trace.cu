@@ -1,10 +1,10 @@
 // trace.cu — batch ray queries: replaces Scene::intersect (reference include/scene.hpp:96-99) for
 // caller-supplied ray batches (BASELINE config 4: the closest-hit microbench).
 //
-// Two-phase, bit-exact: k_closest_octet traverses the 8-wide BVH cooperatively (8 lanes per ray,
-// persistent octets that fetch rays in batches from a global counter) and certifies its answer; rays
-// it cannot certify (bit-equal ties, winner on its own leaf box's entry face) are appended to a
-// fallback list and re-run by k_closest_exact, the flattened reference recursion.
+// Two-phase, bit-exact: k_closest_thread traverses the 8-wide BVH with one ray per lane (persistent warps that
+// refill idle lanes from a warp-local pool of ray indices) and certifies its answer; rays it cannot certify
+// (bit-equal ties, winner on its own leaf box's entry face, stack overflow) are appended to a fallback list and
+// re-run by k_closest_exact, the flattened reference recursion.
 #include <algorithm>
 #include <cstdlib>
 #include "traverse_thread.cuh"
@@ -13,12 +13,8 @@ namespace b2pt {
 
 namespace {
 
-#define B2PT_TRACE_BLOCK 128
-#define B2PT_OCTETS_PER_BLOCK (B2PT_TRACE_BLOCK / 8)
-#define B2PT_RAY_BATCH 8        // rays an octet claims per atomic
-
 __device__ __forceinline__ void flush_counters(TraceCounters* c, unsigned n_nodes, unsigned n_tris) {
-    // warp-aggregate then one atomic per warp (all lanes converged by the caller's __syncwarp)
+    // warp-aggregate then one atomic per warp
     for (int off = 16; off > 0; off >>= 1) {
         n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
         n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
@@ -29,7 +25,7 @@ __device__ __forceinline__ void flush_counters(TraceCounters* c, unsigned n_node
     }
 }
 
-__device__ __forceinline__ RayQ load_ray(const float* __restrict__ o, const float* __restrict__ d,
+__device__ __forceinline__ RayQ load_ray(const DeviceScene& S, const float* __restrict__ o, const float* __restrict__ d,
                                          const float* __restrict__ tmax, long long i) {
     V3 ro = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]);
     V3 rd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
@@ -42,36 +38,6 @@ __device__ __forceinline__ void store_hit(const HitRec& h, long long i, int32_t*
     if (uv) { uv[2 * i] = h.u; uv[2 * i + 1] = h.v; }
 }
 
-// Persistent octets: each claims B2PT_RAY_BATCH consecutive rays at a time.
-template <bool COUNT>
-__global__ void __launch_bounds__(B2PT_TRACE_BLOCK) k_closest_octet(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
-                                                                    const float* __restrict__ tmax, long long n,
-                                                                    int32_t* __restrict__ tri, float* __restrict__ t, float* __restrict__ uv,
-                                                                    unsigned long long* __restrict__ next_ray,
-                                                                    int* __restrict__ fb_count, int* __restrict__ fb_list,
-                                                                    TraceCounters* __restrict__ counters) {
-    __shared__ uint2 stacks[B2PT_OCTETS_PER_BLOCK * B2PT_STACK_PITCH];
-    OctetCtx g = make_octet(stacks);
-    unsigned n_nodes = 0, n_tris = 0;
-    while (true) {
-        unsigned long long base = 0;
-        if (g.gl == 0) base = atomicAdd(next_ray, (unsigned long long)B2PT_RAY_BATCH);
-        base = __shfl_sync(g.gmask, base, g.gbase);
-        if ((long long)base >= n) break;
-        long long end = min((long long)base + B2PT_RAY_BATCH, n);
-        for (long long i = (long long)base; i < end; ++i) {
-            RayQ r = load_ray(o, d, tmax, i);
-            HitRec h;
-            bool ok = closest_octet<COUNT>(S, g, r, h, n_nodes, n_tris);
-            if (g.gl == 0) {
-                store_hit(h, i, tri, t, uv);
-                if (!ok) fb_list[atomicAdd(fb_count, 1)] = (int)i;
-            }
-        }
-    }
-    if (COUNT) { __syncwarp(); flush_counters(counters, n_nodes, n_tris); }
-}
-
 // Exact reference recursion over an index list (fallback) or over the whole batch (list == nullptr).
 __global__ void __launch_bounds__(128) k_closest_exact(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
                                                        const float* __restrict__ tmax, long long n,
@@ -82,48 +48,21 @@ __global__ void __launch_bounds__(128) k_closest_exact(DeviceScene S, const floa
     if (list && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->fallback, (unsigned long long)total);
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
         long long i = list ? list[k] : k;
-        RayQ r = load_ray(o, d, tmax, i);
+        RayQ r = load_ray(S, o, d, tmax, i);
         HitRec h;
         closest_exact_dfs(S, r, h);
         store_hit(h, i, tri, t, uv);
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(B2PT_TRACE_BLOCK) k_any_octet(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
-                                                                const float* __restrict__ tmax, long long n, uint8_t* __restrict__ occ,
-                                                                unsigned long long* __restrict__ next_ray, TraceCounters* __restrict__ counters) {
-    __shared__ uint2 stacks[B2PT_OCTETS_PER_BLOCK * B2PT_STACK_PITCH];
-    OctetCtx g = make_octet(stacks);
-    unsigned n_nodes = 0, n_tris = 0;
-    while (true) {
-        unsigned long long base = 0;
-        if (g.gl == 0) base = atomicAdd(next_ray, (unsigned long long)B2PT_RAY_BATCH);
-        base = __shfl_sync(g.gmask, base, g.gbase);
-        if ((long long)base >= n) break;
-        long long end = min((long long)base + B2PT_RAY_BATCH, n);
-        for (long long i = (long long)base; i < end; ++i) {
-            RayQ r = load_ray(o, d, tmax, i);
-            int res = any_octet<COUNT>(S, g, r, n_nodes, n_tris);
-            if (res < 0) {   // stack overflow (cannot happen below 2^28 triangles): the exact recursion decides
-                HitRec h;
-                closest_exact_dfs(S, r, h);
-                res = h.tri >= 0;
-            }
-            if (g.gl == 0) occ[i] = (uint8_t)res;
-        }
-    }
-    if (COUNT) { __syncwarp(); flush_counters(counters, n_nodes, n_tris); }
-}
-
-
 // ---- one ray per lane, persistent warps with lane refill ------------------------------------------------
 #define B2PT_POOL_CHUNK 256     // ray indices a warp claims per global atomic
 #define B2PT_REFILL_MIN 4       // refill as soon as this many lanes are idle
-#define B2PT_TPS 2              // triangles per step
+#define B2PT_TPS 4              // triangles per step
+#define B2PT_BLOCKS_PER_SM 12   // persistent blocks per SM
 
 template <bool COUNT, int TPS>
-__global__ void __launch_bounds__(B2PT_TBLOCK) k_closest_thread(int refill_min, DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
+__global__ void __launch_bounds__(B2PT_TBLOCK) k_closest_thread(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
                                                         const float* __restrict__ tmax, long long n,
                                                         int32_t* __restrict__ tri, float* __restrict__ t, float* __restrict__ uv,
                                                         unsigned long long* __restrict__ next_ray,
@@ -135,7 +74,7 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_closest_thread(int refill_min, 
     WarpPool pool{0, 0, false};
     long long idx = -1;
     unsigned n_nodes = 0, n_tris = 0;
-    if (S.nwide == 0) {   // empty scene: everything misses
+    if (S.nwide == 0 && S.nhoist == 0) {   // empty scene: everything misses
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
             HitRec h{B2PT_INF, -1, 0.0f, 0.0f};
             store_hit(h, i, tri, t, uv);
@@ -144,11 +83,11 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_closest_thread(int refill_min, 
     }
     while (true) {
         unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
-        if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+        if (idle && (__popc(idle) >= B2PT_REFILL_MIN || idle == 0xffffffffu)) {
             long long got = warp_pool_take<B2PT_POOL_CHUNK>(pool, next_ray, n, idx < 0);
             if (idx < 0 && got >= 0) {
                 idx = got;
-                lane_begin(st, load_ray(o, d, tmax, idx));
+                lane_begin<false, COUNT>(S, st, load_ray(S, o, d, tmax, idx), n_tris);
             }
             if (__ballot_sync(0xffffffffu, idx >= 0) == 0) break;   // nothing left anywhere
         }
@@ -164,7 +103,7 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_closest_thread(int refill_min, 
 }
 
 template <bool COUNT, int TPS>
-__global__ void __launch_bounds__(B2PT_TBLOCK) k_any_thread(int refill_min, DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
+__global__ void __launch_bounds__(B2PT_TBLOCK) k_any_thread(DeviceScene S, const float* __restrict__ o, const float* __restrict__ d,
                                                     const float* __restrict__ tmax, long long n, uint8_t* __restrict__ occ,
                                                     unsigned long long* __restrict__ next_ray, TraceCounters* __restrict__ counters) {
     __shared__ uint2 lane_stacks[B2PT_SSTACK * B2PT_TBLOCK];
@@ -173,19 +112,19 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_any_thread(int refill_min, Devi
     WarpPool pool{0, 0, false};
     long long idx = -1;
     unsigned n_nodes = 0, n_tris = 0;
-    if (S.nwide == 0) {
+    if (S.nwide == 0 && S.nhoist == 0) {
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) occ[i] = 0;
         return;
     }
     while (true) {
         unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
-        if (idle && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+        if (idle && (__popc(idle) >= B2PT_REFILL_MIN || idle == 0xffffffffu)) {
             long long got = warp_pool_take<B2PT_POOL_CHUNK>(pool, next_ray, n, idx < 0);
             if (idx < 0 && got >= 0) {
                 idx = got;
-                lane_begin(st, load_ray(o, d, tmax, idx));
+                if (lane_begin<true, COUNT>(S, st, load_ray(S, o, d, tmax, idx), n_tris)) { occ[idx] = 1; idx = -1; }
             }
-            if (__ballot_sync(0xffffffffu, idx >= 0) == 0) break;
+            if (__ballot_sync(0xffffffffu, idx >= 0) == 0 && pool.exhausted) break;
         }
         if (idx >= 0) {
             int res = lane_any_step<COUNT, TPS>(S, st, n_nodes, n_tris);
@@ -199,24 +138,12 @@ __global__ void __launch_bounds__(B2PT_TBLOCK) k_any_thread(int refill_min, Devi
     if (COUNT) flush_counters(counters, n_nodes, n_tris);
 }
 
-// Experiment knobs (environment, read once): B2PT_TPS triangles per step {1,2,4,8}, B2PT_REFILL idle lanes that
-// trigger a refill, B2PT_BLOCKS_PER_SM persistent blocks per SM.
-struct Tune { int tps, refill, blocks_per_sm; };
-const Tune& tune() {
-    static const Tune t = [] {
-        auto env = [](const char* k, int dflt) { const char* v = std::getenv(k); return v ? std::atoi(v) : dflt; };
-        return Tune{env("B2PT_TPS", 4), env("B2PT_REFILL", 4), env("B2PT_BLOCKS_PER_SM", 12)};
-    }();
-    return t;
-}
-
 }  // namespace
 
 int launch_trace_closest(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n,
                          int32_t* d_tri, float* d_t, float* d_uv) {
     if (n <= 0) return B2PT_OK;
     cudaStream_t st = ctx->stream;
-    const int B = B2PT_TRACE_BLOCK;
     // Rays are processed in launches of at most 2^30 so the int fallback list can index them.
     const int64_t chunk = 1ll << 30;
     unsigned long long* next_ray = reinterpret_cast<unsigned long long*>(ctx->d_fallback_count + 2);
@@ -234,24 +161,11 @@ int launch_trace_closest(b2pt_ctx* ctx, const float* d_o, const float* d_d, cons
             int rc = scratch_reserve(ctx, 0, sizeof(int) * (size_t)m, &fb);
             if (rc) return rc;
             B2PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fallback_count, 0, 64, st));
-            int64_t octets = (m + B2PT_RAY_BATCH - 1) / B2PT_RAY_BATCH;
-            unsigned grid = (unsigned)std::min<int64_t>((octets + B2PT_OCTETS_PER_BLOCK - 1) / B2PT_OCTETS_PER_BLOCK, (int64_t)ctx->sm_count * 16);
-            if (ctx->flags & B2PT_FLAG_OCTET) {
-                if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
-                    k_closest_octet<true><<<grid, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
-                else
-                    k_closest_octet<false><<<grid, B, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
-            } else {
-                const Tune tu = tune();
-                unsigned tgrid = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * tu.blocks_per_sm);
-#define LAUNCH_CT(C, T) k_closest_thread<C, T><<<tgrid, 128, 0, st>>>(tu.refill, ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters)
-                if (ctx->flags & B2PT_FLAG_COUNT_FETCHES) LAUNCH_CT(true, 2);
-                else if (tu.tps == 1) LAUNCH_CT(false, 1);
-                else if (tu.tps == 4) LAUNCH_CT(false, 4);
-                else if (tu.tps == 8) LAUNCH_CT(false, 8);
-                else LAUNCH_CT(false, 2);
-#undef LAUNCH_CT
-            }
+            unsigned tgrid = (unsigned)std::min<int64_t>((m + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (int64_t)ctx->sm_count * B2PT_BLOCKS_PER_SM);
+            if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
+                k_closest_thread<true, B2PT_TPS><<<tgrid, B2PT_TBLOCK, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
+            else
+                k_closest_thread<false, B2PT_TPS><<<tgrid, B2PT_TBLOCK, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, next_ray, ctx->d_fallback_count, (int*)fb, ctx->d_counters);
             k_closest_exact<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->scene, o, d, tm, m, tri, t, uv, ctx->d_fallback_count, (const int*)fb, ctx->d_counters);
             ctx->stats.kernel_launches += 2;
         }
@@ -262,31 +176,17 @@ int launch_trace_closest(b2pt_ctx* ctx, const float* d_o, const float* d_d, cons
 
 int launch_trace_any(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n, uint8_t* d_occ) {
     if (n <= 0) return B2PT_OK;
-    const int B = B2PT_TRACE_BLOCK;
     const int64_t chunk = 1ll << 30;
     unsigned long long* next_ray = reinterpret_cast<unsigned long long*>(ctx->d_fallback_count + 2);
     for (int64_t off = 0; off < n; off += chunk) {
         int64_t m = std::min(chunk, n - off);
         const float* tm = d_tmax ? d_tmax + off : nullptr;
         B2PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fallback_count, 0, 64, ctx->stream));
-        int64_t octets = (m + B2PT_RAY_BATCH - 1) / B2PT_RAY_BATCH;
-        unsigned grid = (unsigned)std::min<int64_t>((octets + B2PT_OCTETS_PER_BLOCK - 1) / B2PT_OCTETS_PER_BLOCK, (int64_t)ctx->sm_count * 16);
-        if (ctx->flags & B2PT_FLAG_OCTET) {
-            if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
-                k_any_octet<true><<<grid, B, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
-            else
-                k_any_octet<false><<<grid, B, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
-        } else {
-            const Tune tu = tune();
-            unsigned tgrid = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)ctx->sm_count * tu.blocks_per_sm);
-#define LAUNCH_AT(C, T) k_any_thread<C, T><<<tgrid, 128, 0, ctx->stream>>>(tu.refill, ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters)
-            if (ctx->flags & B2PT_FLAG_COUNT_FETCHES) LAUNCH_AT(true, 2);
-            else if (tu.tps == 1) LAUNCH_AT(false, 1);
-            else if (tu.tps == 4) LAUNCH_AT(false, 4);
-            else if (tu.tps == 8) LAUNCH_AT(false, 8);
-            else LAUNCH_AT(false, 2);
-#undef LAUNCH_AT
-        }
+        unsigned tgrid = (unsigned)std::min<int64_t>((m + B2PT_TBLOCK - 1) / B2PT_TBLOCK, (int64_t)ctx->sm_count * B2PT_BLOCKS_PER_SM);
+        if (ctx->flags & B2PT_FLAG_COUNT_FETCHES)
+            k_any_thread<true, B2PT_TPS><<<tgrid, B2PT_TBLOCK, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
+        else
+            k_any_thread<false, B2PT_TPS><<<tgrid, B2PT_TBLOCK, 0, ctx->stream>>>(ctx->scene, d_o + 3 * off, d_d + 3 * off, tm, m, d_occ + off, next_ray, ctx->d_counters);
         ctx->stats.kernel_launches += 1;
         B2PT_CUDA(ctx, cudaGetLastError());
     }

@@ -1,17 +1,25 @@
-// traverse.cuh — device traversal routines shared by the query kernels (trace.cu) and the
+// traverse.cuh — device traversal building blocks shared by the query kernels (trace.cu) and the
 // wavefront renderer (render.cu).  Replaces BVH::intersect / intersectNode (reference
-// include/bvh.hpp:37-39, :74-116) with three routines:
+// include/bvh.hpp:37-39, :74-116).
 //
 //   closest_exact_dfs  the reference recursion itself, flattened: left-then-right DFS over the
 //                      implicit reference tree, global tMax shrink, reference tie rules.  Slow
 //                      (no ordering, binary tree) but exact by construction; used for the rays the
-//                      fast kernel cannot certify, and alone under B2PT_FLAG_EXACT_ONLY.
-//   closest_octet      ordered, warp-cooperative (8 lanes per ray) traversal of the 8-wide collapse.
-//                      Returns the candidate plus a "certified" verdict: certified
-//                      results are provably what the reference returns; the rest go to
-//                      closest_exact_dfs.
-//   any_octet          boolean occlusion query (shadow rays, renderer.hpp:274-278), exact without
-//                      any fallback because its answer does not depend on traversal history.
+//                      fast kernels cannot certify, and alone under B2PT_FLAG_EXACT_ONLY.
+//   node_test4         the reference slab test (aabb.hpp:13-25) of four children of a wide node
+//   box_pass           the same test for one box: the certificate, the hoisted leaves, the exact recursion
+//
+// Exactness.  A triangle X is a CANDIDATE for a ray iff the exact box of X's reference leaf
+// passes the reference slab test at the ray's initial tMax (T0) and Triangle::intersect accepts X in
+// [tMin, T0].  The traversal tree only has to be CONSERVATIVE above the leaves: its inner boxes are exact min/max
+// unions of exact leaf boxes, every box is tested with the reference's own arithmetic (node_test4), and that
+// arithmetic is monotone — a superset box passes whenever a box inside it does — so a visible leaf is never culled,
+// whatever the shape of the tree, and a visited leaf is visible by the very test the reference applies.
+//
+// (Measured and dropped in round 2: a one-FMA-per-plane slab test, fma(plane, 1/d, -o/d -+ slack), made provably
+// conservative with per-ray slack constants and re-checked exactly per accepted triangle.  21 instead of 32
+// arithmetic instructions per child, but six more live registers per ray: closest hit 1760 -> 1690, any-hit
+// 2750 -> 2230 Mrays/s, 1M-triangle render 216 -> 208 Msamples/s.  profiles/r02_experiments.md.)
 #pragma once
 #include "ctx.cuh"
 
@@ -23,13 +31,24 @@ struct RayQ {
     float T0;     // initial ray.tMax
 };
 
-__device__ __forceinline__ RayQ make_rayq(V3 o, V3 d_unnormalised, float T0) {
+__device__ __forceinline__ RayQ make_rayq_normalised(V3 o, V3 d, float T0) {
     RayQ r;
-    r.o = o;
-    r.d = vnormalize(d_unnormalised);
+    r.o = o; r.d = d; r.T0 = T0;
     r.invD = mk3(B2PT_DIV(1.0f, r.d.x), B2PT_DIV(1.0f, r.d.y), B2PT_DIV(1.0f, r.d.z));
-    r.T0 = T0;
     return r;
+}
+
+__device__ __forceinline__ RayQ make_rayq(V3 o, V3 d_unnormalised, float T0) {
+    return make_rayq_normalised(o, vnormalize(d_unnormalised), T0);
+}
+
+// Distance cull of closest-hit queries: once a candidate with distance t is known, subtrees entered later than
+// t * (1 + 2^-10) + 2^-12 * (R + |o|) are skipped (R = S.coord_bound, the largest |coordinate| in the scene).  The
+// computed t of a Möller–Trumbore hit is off by an ABSOLUTE amount that grows with the distance between the origin and
+// the triangle, not with t, so the slack has a part proportional to the coordinate range as well as a relative one.
+__device__ __forceinline__ float cull_after_hit(const DeviceScene& S, const RayQ& r, float t) {
+    const float reach = S.coord_bound + fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z));
+    return fminf(r.T0, __fmaf_rn(t, 0.0009765625f, t) + reach * 2.44140625e-4f);
 }
 
 // A ray with a non-finite component never hits anything in the reference.
@@ -43,50 +62,35 @@ __device__ __forceinline__ RayQ make_rayq(V3 o, V3 d_unnormalised, float T0) {
 //  * infinite direction (normalising a vector whose squared length underflows): invD = 0, every t0/t1 is 0 or
 //    NaN, the root box ends with tMax = 0 <= tMin.
 // The answer is a miss / "not occluded" — in the first two cases after walking most of the tree.  The kernels
-// return it at once: such a ray would also pass the boxes of EMPTY child slots (lo = +inf, hi = -inf give NaN
-// slabs), which are not valid triangle ranges, and would hold its warp for a full-scene walk.  These rays do
-// occur: a zero interpolated normal makes the dielectric branch's refract() return vec3(0) (renderer.hpp:233),
-// whose Ray ctor normalisation is NaN (ray.hpp:12).
+// return it at once: such a ray would also pass the boxes of EMPTY child slots (NaN slabs), which are not valid
+// triangle ranges, and would hold its warp for a full-scene walk.  These rays do occur: a zero interpolated normal
+// makes the dielectric branch's refract() return vec3(0) (renderer.hpp:233), whose Ray ctor normalisation is NaN
+// (ray.hpp:12).
 __device__ __forceinline__ bool ray_has_nan(const RayQ& r) {
     const float inf = B2PT_INF;
     return !((fabsf(r.o.x) < inf) & (fabsf(r.o.y) < inf) & (fabsf(r.o.z) < inf) &
              (fabsf(r.d.x) < inf) & (fabsf(r.d.y) < inf) & (fabsf(r.d.z) < inf));
 }
 
-__device__ __forceinline__ bool box_pass(float4 lo, float4 hi, const RayQ& r, float T, float& entry) {
+// The reference slab test (aabb.hpp:13-25), bit for bit.
+__device__ __forceinline__ bool box_pass(float4 lo, float4 hi, V3 o, V3 invD, float T) {
     float tmin = B2PT_TMIN, tmax = T;
-    slab_axis(lo.x, hi.x, r.o.x, r.invD.x, tmin, tmax);
-    slab_axis(lo.y, hi.y, r.o.y, r.invD.y, tmin, tmax);
-    slab_axis(lo.z, hi.z, r.o.z, r.invD.z, tmin, tmax);
-    entry = tmin;
+    slab_axis(lo.x, hi.x, o.x, invD.x, tmin, tmax);
+    slab_axis(lo.y, hi.y, o.y, invD.y, tmin, tmax);
+    slab_axis(lo.z, hi.z, o.z, invD.z, tmin, tmax);
     return tmax > tmin;
 }
 
-// Latency hints (ncu: long-scoreboard is the top stall of every traversal kernel on the 1M-triangle scene;
-// a leaf's triangles span 3-4 cache lines that the test loop would otherwise miss on one after the other).
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-// Lines 2.. of a leaf's triangle run (the loop's first load fetches line 1 itself).
-__device__ __forceinline__ void prefetch_leaf_rest(const DeviceScene& S, int first, int cnt) {
-    const char* b = reinterpret_cast<const char*>(S.tri + 3ll * first);
-    const int bytes = cnt * 48;
-    if (bytes > 128) prefetch_l1(b + 128);
-    if (bytes > 256) prefetch_l1(b + 256);
-    prefetch_l1(b + bytes - 16);
-}
-// What a stack entry will touch first when it is popped: an inner node's 224 B or a leaf's first triangles.
-__device__ __forceinline__ void prefetch_child(const DeviceScene& S, uint32_t code) {
-    if (code & B2PT_CHILD_LEAF) {
-        prefetch_l1(S.tri + 3ll * (code & 0x0FFFFFFF));
-    } else {
-        const char* b = reinterpret_cast<const char*>(S.wide + code);
-        prefetch_l1(b);
-        prefetch_l1(b + 208);
-    }
+// Does the exact box of reference leaf `leaf` pass the reference slab test with ray.tMax == T?
+__device__ __forceinline__ bool leaf_visible(const DeviceScene& S, int leaf, const RayQ& r, float T) {
+    return box_pass(__ldg(&S.leaf_lo[leaf]), __ldg(&S.leaf_hi[leaf]), r.o, r.invD, T);
 }
 
 // Children 4k..4k+3 of a wide node, planes ordered along the ray: WideNode is lox|loy|loz|hix|hiy|hiz (8 floats
 // each = two float4), so the near plane of axis a is float4 index 2a + (invD[a] < 0 ? 6 : 0) + k and the far plane
-// the other one.  Slab-tests the four boxes at T0; pass[s] / tmin[s] per child.
+// the other one.  Selecting the PLANE by the ray's sign once per node (an address offset) instead of swapping the two
+// products per child (aabb.hpp:17) gives bit-identical t values.  Slab-tests the four boxes at T0 with the reference's
+// arithmetic; pass[s] / tmin[s] per child.
 struct Node4 { float tmin[4]; bool pass[4]; uint32_t code[4]; };
 __device__ __forceinline__ void node_test4(const WideNode* nd, int k, const RayQ& r, Node4& out) {
     const float4* p = reinterpret_cast<const float4*>(nd);
@@ -108,10 +112,12 @@ __device__ __forceinline__ void node_test4(const WideNode* nd, int k, const RayQ
     }
 }
 
-__device__ __forceinline__ bool tri_fetch_test(const DeviceScene& S, int i, const RayQ& r, float tmax, float& t, float& u, float& v) {
+// Triangle i (reference id): Möller–Trumbore exactly as the reference computes it; `leaf` = its reference leaf.
+__device__ __forceinline__ bool tri_fetch_test(const DeviceScene& S, int i, const RayQ& r, float tmax, float& t, float& u, float& v, int& leaf) {
     float4 a = __ldg(&S.tri[3ll * i + 0]);
     float4 b = __ldg(&S.tri[3ll * i + 1]);
     float4 c = __ldg(&S.tri[3ll * i + 2]);
+    leaf = __float_as_int(a.w);
     return tri_test(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), r.o, r.d, tmax, t, u, v);
 }
 
@@ -128,15 +134,14 @@ __device__ __forceinline__ void closest_exact_dfs(const DeviceScene& S, const Ra
     int sp = 0;
     int node = 0;
     while (true) {
-        float entry;
         bool descend = false;
-        if (box_pass(__ldg(&S.node_lo[node]), __ldg(&S.node_hi[node]), r, tmax, entry)) {
+        if (box_pass(__ldg(&S.node_lo[node]), __ldg(&S.node_hi[node]), r.o, r.invD, tmax)) {
             int4 info = __ldg(&S.node_info[node]);
             if (info.w >= 0) {
                 float lt = B2PT_INF, lu = 0.0f, lv = 0.0f; int ltri = -1;
                 for (int i = info.x; i < info.y; ++i) {
-                    float t, u, v;
-                    if (tri_fetch_test(S, i, r, tmax, t, u, v)) {
+                    float t, u, v; int leaf;
+                    if (tri_fetch_test(S, i, r, tmax, t, u, v, leaf)) {
                         if (t < lt) { lt = t; lu = u; lv = v; ltri = i; tmax = t; }
                     }
                 }
@@ -151,190 +156,6 @@ __device__ __forceinline__ void closest_exact_dfs(const DeviceScene& S, const Ra
             if (sp == 0) break;
             node = stack[--sp];
         }
-    }
-}
-
-// =====================================================================================================
-// Warp-cooperative traversal: 8 lanes ("an octet") per ray.
-//
-// The per-thread routines above execute with ~4 of 32 lanes active (ncu: profiles/r01_ncu_closest_v1_*):
-// every lane walks its own tree, so node steps, leaf steps, sorting and popping all diverge.  Here a ray
-// is owned by 8 consecutive lanes that always do the same thing: in a wide node each lane slab-tests ONE
-// child box (a coalesced 32-byte read per plane), in a reference leaf each lane runs Möller–Trumbore on
-// ONE triangle (leaves hold <= 8).  Hit ordering, stack pushes and the closest-hit reduction are
-// __ballot_sync / __shfl_sync operations inside the octet; the traversal stack is one shared-memory array
-// per octet.  The four octets of a warp are independent rays (sub-warp masks), so divergence is only
-// "octet A is in a node while octet B is in a leaf".
-//
-// Closest hit — candidate set: triangles whose reference leaf box passes the reference slab test at T0
-// (exact: the leaf's box IS the wide child's box, tested with the reference arithmetic) and that
-// Triangle::intersect accepts in [tMin, T0].  Subtrees are culled when their box fails at T0 (exact and
-// monotone: a superset box passes whenever a leaf inside it passes) or when their entry distance exceeds
-// the current best by more than a relative 2^-10.  The result is CERTIFIED to be the reference's answer
-// when it is a miss (no candidate), or a unique minimum-t candidate whose leaf box still passes the slab
-// test at T = t; everything else is re-run by closest_exact_dfs.
-//
-// Occlusion (renderer.hpp:274-278 asks only whether Scene::intersect returns true): before the first
-// accepted triangle ray.tMax still has its initial value, so the answer is "does a triangle exist whose
-// reference leaf box passes at T0 and which Triangle::intersect accepts in [tMin, T0]" — independent of
-// traversal order, exact without any fallback.
-// =====================================================================================================
-#define B2PT_STACK 64            // entries per octet; deepest push chain is 7 per wide level, <= 9 levels
-#define B2PT_STACK_PITCH 65      // +1 entry of padding: octets' stacks start in different banks
-
-struct OctetCtx {
-    unsigned gmask;      // the octet's 8 lanes within the warp
-    int gl;              // lane within the octet, 0..7
-    int gbase;           // first lane of the octet within the warp
-    uint2* stack;        // shared-memory stack of this octet
-};
-
-__device__ __forceinline__ OctetCtx make_octet(uint2* block_stacks) {
-    OctetCtx c;
-    int lane = threadIdx.x & 31;
-    c.gl = lane & 7;
-    c.gbase = lane & ~7;
-    c.gmask = 0xffu << c.gbase;
-    c.stack = block_stacks + (threadIdx.x >> 3) * B2PT_STACK_PITCH;
-    return c;
-}
-
-// One lane's slab test of child `gl` of a wide node.
-__device__ __forceinline__ bool octet_child_test(const WideNode* nd, int gl, const RayQ& r, float& tmin, uint32_t& code) {
-    float lx = __ldg(&nd->lox[gl]), ly = __ldg(&nd->loy[gl]), lz = __ldg(&nd->loz[gl]);
-    float hx = __ldg(&nd->hix[gl]), hy = __ldg(&nd->hiy[gl]), hz = __ldg(&nd->hiz[gl]);
-    code = __ldg(&nd->child[gl]);
-    float tmax = r.T0;
-    tmin = B2PT_TMIN;
-    slab_axis(lx, hx, r.o.x, r.invD.x, tmin, tmax);
-    slab_axis(ly, hy, r.o.y, r.invD.y, tmin, tmax);
-    slab_axis(lz, hz, r.o.z, r.invD.z, tmin, tmax);
-    return tmax > tmin;
-}
-
-// Closest hit, cooperative.  All 8 lanes of the octet call this with the same ray and get the same result.
-// Returns the certificate (true = provably the reference's answer).
-template <bool COUNT>
-__device__ __forceinline__ bool closest_octet(const DeviceScene& S, const OctetCtx& g, const RayQ& r, HitRec& out,
-                                              unsigned& n_nodes, unsigned& n_tris) {
-    out.t = B2PT_INF; out.tri = -1; out.u = 0.0f; out.v = 0.0f;
-    if (S.nwide == 0 || ray_has_nan(r)) return true;
-    bool tie = false, overflow = false;
-    float cull = r.T0;
-    int sp = 0;
-    uint32_t cur = 0;
-    while (true) {
-        if (!(cur & B2PT_CHILD_LEAF)) {
-            if (COUNT && g.gl == 0) ++n_nodes;
-            float tmin; uint32_t code;
-            bool hit = octet_child_test(&S.wide[cur], g.gl, r, tmin, code) && tmin <= cull;
-            unsigned hm = (__ballot_sync(g.gmask, hit) >> g.gbase) & 0xffu;
-            int n = __popc(hm);
-            if (n > 0) {
-                // rank = number of hit children that must sit BELOW me on the stack (farther first)
-                int rank = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float tj = __shfl_sync(g.gmask, tmin, g.gbase + j);
-                    bool below = (tj > tmin) || (tj == tmin && j < g.gl);
-                    rank += (((hm >> j) & 1u) && below) ? 1 : 0;
-                }
-                if (sp + n - 1 > B2PT_STACK) { overflow = true; break; }
-                if (hit && rank < n - 1) g.stack[sp + rank] = make_uint2(code, __float_as_uint(tmin));
-                // the nearest child (rank n-1) is visited next without going through the stack
-                unsigned nm = (__ballot_sync(g.gmask, hit && rank == n - 1) >> g.gbase) & 0xffu;
-                cur = __shfl_sync(g.gmask, code, g.gbase + __ffs(nm) - 1);
-                sp += n - 1;
-                __syncwarp(g.gmask);
-                continue;
-            }
-        } else {
-            int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;
-            float t = B2PT_INF, u = 0.0f, v = 0.0f;
-            bool acc = false;
-            if (g.gl < cnt) {
-                if (COUNT) ++n_tris;
-                acc = tri_fetch_test(S, first + g.gl, r, r.T0, t, u, v);
-                if (!acc) t = B2PT_INF;
-            }
-            unsigned am = (__ballot_sync(g.gmask, acc) >> g.gbase) & 0xffu;
-            if (am) {
-                // octet minimum of t
-                float m = t;
-                m = fminf(m, __shfl_xor_sync(g.gmask, m, 1));
-                m = fminf(m, __shfl_xor_sync(g.gmask, m, 2));
-                m = fminf(m, __shfl_xor_sync(g.gmask, m, 4));
-                unsigned wm = (__ballot_sync(g.gmask, acc && t == m) >> g.gbase) & 0xffu;
-                if (m < out.t) {
-                    int w = __ffs(wm) - 1;   // first triangle of the leaf with the minimum t (bvh.hpp:88)
-                    out.t = m;
-                    out.tri = first + w;
-                    out.u = __shfl_sync(g.gmask, u, g.gbase + w);
-                    out.v = __shfl_sync(g.gmask, v, g.gbase + w);
-                    tie = __popc(wm) > 1;
-                    cull = fminf(r.T0, __fmaf_rn(m, 0.0009765625f, m));
-                } else if (m == out.t) {
-                    tie = true;
-                }
-            }
-        }
-        // pop the nearest pending subtree that can still matter
-        bool got = false;
-        while (sp > 0) {
-            --sp;
-            uint2 e = g.stack[sp];
-            if (__uint_as_float(e.y) <= cull) { cur = e.x; got = true; break; }
-        }
-        if (!got) break;
-    }
-    if (overflow) return false;
-    if (out.tri < 0) return true;
-    if (tie) return false;
-    int leaf = __float_as_int(__ldg(&S.tri[3ll * out.tri]).w);
-    float entry;
-    return box_pass(__ldg(&S.leaf_lo[leaf]), __ldg(&S.leaf_hi[leaf]), r, out.t, entry);
-}
-
-// Occlusion query, cooperative.  Returns 1 occluded, 0 free, -1 stack overflow (caller must use the exact path).
-template <bool COUNT>
-__device__ __forceinline__ int any_octet(const DeviceScene& S, const OctetCtx& g, const RayQ& r, unsigned& n_nodes, unsigned& n_tris) {
-    if (S.nwide == 0 || ray_has_nan(r)) return 0;
-    int sp = 0;
-    uint32_t cur = 0;
-    while (true) {
-        if (!(cur & B2PT_CHILD_LEAF)) {
-            if (COUNT && g.gl == 0) ++n_nodes;
-            float tmin; uint32_t code;
-            bool hit = octet_child_test(&S.wide[cur], g.gl, r, tmin, code);
-            unsigned hm = (__ballot_sync(g.gmask, hit) >> g.gbase) & 0xffu;
-            int n = __popc(hm);
-            if (n > 0) {
-                if (sp + n - 1 > B2PT_STACK) return -1;
-                // leaves first: they can end the query at once (top of stack = visited next)
-                bool leaf = (code & B2PT_CHILD_LEAF) != 0;
-                unsigned lm = (__ballot_sync(g.gmask, hit && leaf) >> g.gbase) & 0xffu;
-                unsigned below_me = (1u << g.gl) - 1u;
-                int nl = __popc(lm);
-                int pos = leaf ? (n - nl) + __popc(lm & below_me) : __popc((hm & ~lm) & below_me);
-                if (hit && pos < n - 1) g.stack[sp + pos] = make_uint2(code, 0u);
-                unsigned nm = (__ballot_sync(g.gmask, hit && pos == n - 1) >> g.gbase) & 0xffu;
-                cur = __shfl_sync(g.gmask, code, g.gbase + __ffs(nm) - 1);
-                sp += n - 1;
-                __syncwarp(g.gmask);
-                continue;
-            }
-        } else {
-            int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;
-            bool acc = false;
-            if (g.gl < cnt) {
-                float t, u, v;
-                if (COUNT) ++n_tris;
-                acc = tri_fetch_test(S, first + g.gl, r, r.T0, t, u, v);
-            }
-            if (__ballot_sync(g.gmask, acc) & g.gmask) return 1;
-        }
-        if (sp == 0) return 0;
-        cur = g.stack[--sp].x;
     }
 }
 

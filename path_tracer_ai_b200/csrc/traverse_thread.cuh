@@ -8,13 +8,13 @@
 // step per loop iteration — one wide node, or up to TPS triangles of the current leaf — and the kernel
 // loop refills idle lanes from a warp-local pool of ray indices between steps.
 //
-// Exactness is that of DESIGN.md §2: same candidate set, same certificate as the cooperative variant.
+// Exactness is that of DESIGN.md §2 / traverse.cuh: same candidate set, same certificate as the run-to-completion variant.
 #pragma once
 #include "traverse.cuh"
 
 namespace b2pt {
 
-#define B2PT_TSTACK 64   // 7 pushes per wide level, <= 9 levels below 2^28 triangles
+#define B2PT_TSTACK 64   // deeper pushes set `overflow`: the ray is then answered by the exact reference recursion
 #define B2PT_SSTACK 16   // entries of each lane's stack that live in shared memory (the rest: local memory)
 #define B2PT_TBLOCK 128  // block size of the per-lane kernels (stride of the shared stack layout)
 
@@ -34,6 +34,7 @@ struct LaneStack {
 struct LaneState {
     RayQ r;
     HitRec best;
+    int best_leaf;
     float cull;
     int sp;
     uint32_t cur;          // inner wide node to expand (valid when tri_next == tri_end)
@@ -44,9 +45,13 @@ struct LaneState {
     LaneStack stack;       // (child code, entry distance bits)
 };
 
-__device__ __forceinline__ void lane_begin(LaneState& st, const RayQ& r) {
+// Starts a query.  ANY: occlusion query — returns true when a hoisted leaf already occludes the ray.  The hoisted
+// leaves (ctx.cuh) are tested here, by all the lanes a refill starts together.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool lane_begin(const DeviceScene& S, LaneState& st, const RayQ& r, unsigned& n_tris) {
     st.r = r;
     st.best.t = B2PT_INF; st.best.tri = -1; st.best.u = 0.0f; st.best.v = 0.0f;
+    st.best_leaf = -1;
     st.cull = r.T0;
     st.sp = 0;
     st.cur = 0;
@@ -54,6 +59,26 @@ __device__ __forceinline__ void lane_begin(LaneState& st, const RayQ& r) {
     st.tie = false;
     st.overflow = false;
     st.dead = ray_has_nan(r);
+    if (st.dead) return false;
+    for (int h = 0; h < S.nhoist; ++h) {
+        if (!leaf_visible(S, S.hoist_leaf[h], r, r.T0)) continue;
+        const int first = S.hoist_code[h] & 0x0FFFFFFF, cnt = ((S.hoist_code[h] >> 28) & 7) + 1;
+        for (int i = first; i < first + cnt; ++i) {
+            float t, u, v; int leaf;
+            if (COUNT) ++n_tris;
+            if (tri_fetch_test(S, i, r, r.T0, t, u, v, leaf)) {
+                if (ANY) return true;
+                if (t < st.best.t) {
+                    st.best.t = t; st.best.tri = i; st.best.u = u; st.best.v = v; st.tie = false; st.best_leaf = leaf;
+                    st.cull = cull_after_hit(S, r, t);
+                } else if (t == st.best.t) {
+                    st.tie = true;
+                }
+            }
+        }
+    }
+    if (S.nwide == 0) st.dead = true;   // nothing below the hoisted leaves
+    return false;
 }
 
 // Expands wide node st.cur: slab-tests the 8 children at T0 and pushes the survivors sorted by entry
@@ -115,14 +140,14 @@ __device__ __forceinline__ bool lane_closest_step(const DeviceScene& S, LaneStat
 #pragma unroll
         for (int k = 0; k < TPS; ++k) {
             if (st.tri_next < st.tri_end) {
-                float t, u, v;
+                float t, u, v; int leaf;
                 if (COUNT) ++n_tris;
                 int i = st.tri_next++;
-                if (tri_fetch_test(S, i, st.r, st.r.T0, t, u, v)) {
+                if (tri_fetch_test(S, i, st.r, st.r.T0, t, u, v, leaf) && t <= st.best.t) {
                     if (t < st.best.t) {
-                        st.best.t = t; st.best.tri = i; st.best.u = u; st.best.v = v; st.tie = false;
-                        st.cull = fminf(st.r.T0, __fmaf_rn(t, 0.0009765625f, t));
-                    } else if (t == st.best.t) {
+                        st.best.t = t; st.best.tri = i; st.best.u = u; st.best.v = v; st.tie = false; st.best_leaf = leaf;
+                        st.cull = cull_after_hit(S, st.r, t);
+                    } else {
                         st.tie = true;
                     }
                 }
@@ -141,23 +166,21 @@ __device__ __forceinline__ bool lane_certify(const DeviceScene& S, const LaneSta
     if (st.overflow) return false;
     if (st.best.tri < 0) return true;
     if (st.tie) return false;
-    int leaf = __float_as_int(__ldg(&S.tri[3ll * st.best.tri]).w);
-    float entry;
-    return box_pass(__ldg(&S.leaf_lo[leaf]), __ldg(&S.leaf_hi[leaf]), st.r, st.best.t, entry);
+    return leaf_visible(S, st.best_leaf, st.r, st.best.t);
 }
 
 // One bounded step of an occlusion query.  Returns 0 = keep going, 1 = finished & occluded, 2 = finished
 // & free, 3 = stack overflow (caller must use the exact recursion).
 template <bool COUNT, int TPS>
 __device__ __forceinline__ int lane_any_step(const DeviceScene& S, LaneState& st, unsigned& n_nodes, unsigned& n_tris) {
-    if (st.dead) return 2;
+    if (st.dead) return st.overflow ? 3 : 2;
     if (st.tri_next < st.tri_end) {
 #pragma unroll
         for (int k = 0; k < TPS; ++k) {
             if (st.tri_next < st.tri_end) {
-                float t, u, v;
+                float t, u, v; int leaf;
                 if (COUNT) ++n_tris;
-                if (tri_fetch_test(S, st.tri_next++, st.r, st.r.T0, t, u, v)) return 1;
+                if (tri_fetch_test(S, st.tri_next++, st.r, st.r.T0, t, u, v, leaf)) return 1;
             }
         }
         if (st.tri_next < st.tri_end) return 0;
