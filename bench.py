@@ -344,6 +344,7 @@ def main():
     ap.add_argument("--c4-check", type=int, default=4_000_000, help="rays of the microbench compared with the reference CPU BVH")
     ap.add_argument("--max-paths", type=int, default=DEFAULT_MAX_PATHS)
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (reported in config.spp)")
+    ap.add_argument("--flags", type=int, default=0, help="B2PT_FLAG_* bits for the timed engine (experiments; 0 = product defaults)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -382,7 +383,7 @@ def main():
     kind_s, payload = prebuild_arrays(args.workload, tmp.name)
     sc = make_scene(kind_s, payload)
     cam = pt.Camera()
-    eng = pt.Engine(device=local_rank, max_paths=args.max_paths)
+    eng = pt.Engine(device=local_rank, flags=args.flags, max_paths=args.max_paths)
     eng.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
     build_s = eng.stats()["build_seconds"]
 

@@ -89,7 +89,9 @@ typedef struct b2pt_config {
 
 #define B2PT_FLAG_COUNT_FETCHES 1  /* instrumented traversal: count node / triangle fetches (slower) */
 #define B2PT_FLAG_EXACT_ONLY 2     /* closest-hit queries use only the exact reference-order DFS kernel */
-#define B2PT_FLAG_NO_LEARN_ORDER 8 /* do not re-order wide-node children by measured occlusion rate after the first batch */
+#define B2PT_FLAG_LANE_KERNELS 4    /* occlusion queries of incoherent batches use the one-ray-per-lane kernels instead of the phase-split pool kernels */
+#define B2PT_FLAG_POOL_EXTEND 16    /* closest-hit queries of incoherent batches use the pool kernels too (measured: no faster) */
+#define B2PT_FLAG_NO_LEARN_ORDER 8  /* do not re-order wide-node children by measured occlusion rate after the first batch */
 
 /* Counters of the last trace / render call. */
 typedef struct b2pt_stats {

@@ -16,7 +16,9 @@ LIB_PATH = os.environ.get("B2PT_LIB") or os.path.join(_HERE, "libb2pt.so")   # B
 DIFFUSE, SPECULAR, DIELECTRIC = 0, 1, 2
 FLAG_COUNT_FETCHES = 1
 FLAG_EXACT_ONLY = 2
+FLAG_LANE_KERNELS = 4
 FLAG_NO_LEARN_ORDER = 8
+FLAG_POOL_EXTEND = 16
 
 
 class Material(C.Structure):

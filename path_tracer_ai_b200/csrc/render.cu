@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "traverse_pool.cuh"
 #include "traverse_rtc.cuh"
 
 namespace b2pt {
@@ -285,6 +286,57 @@ __global__ void __launch_bounds__(B2PT_SHD_BLOCK) k_shadow_rtc(DeviceScene S, Wa
         }
         if ((threadIdx.x & 31) == 0) { atomicAdd(&tc->node_fetches, (unsigned long long)n_nodes); atomicAdd(&tc->tri_fetches, (unsigned long long)n_tris); }
     }
+}
+
+// ---- incoherent bounces: several rays per lane, phase-split steps (traverse_pool.cuh) -------------------------------
+// Same queues, same results as k_extend_rtc<.., false> / k_shadow_rtc; used from the first bounce on in scenes large
+// enough for the rays of a warp to diverge.
+struct IoExtend {
+    Wave W; const int* list;
+    __device__ __forceinline__ bool load(const DeviceScene&, long long k, V3& ro, V3& rd, float& T0, int& tag) const {
+        const int p = list ? list[k] : (int)k;
+        float4 o4 = W.ro[p], d4 = W.rd[p];
+        ro = f4v(o4); rd = f4v(d4); T0 = B2PT_INF; tag = p;   // rd is the Ray ctor's normalised direction already
+        return true;
+    }
+    __device__ __forceinline__ void store_closest(int p, const HitRec& h, bool certified) const {
+        W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+        if (!certified) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
+    }
+    __device__ __forceinline__ void store_any(int, bool) const {}
+};
+struct IoShadow {
+    Wave W;
+    __device__ __forceinline__ bool load(const DeviceScene& S, long long k, V3& ro, V3& rd, float& T0, int& tag) const {
+        const int e = W.q_shadow[k], nl = S.nlight;
+        const int p = e / nl, l = e - p * nl;
+        float4 g0 = W.g0[p], g1 = W.g1[p];
+        V3 P = f4v(g0), n = f4v(g1);
+        const DLight& lt = S.lights[l];
+        V3 lightDir = vsub(mk3(lt.px, lt.py, lt.pz), P);
+        float dist = vlength(lightDir);
+        ro = vadd(P, vmuls(n, 0.001f));                 // renderer.hpp:271-275
+        rd = vnormalize(vnormalize(lightDir));          // :271, then the Ray ctor (ray.hpp:12)
+        T0 = B2PT_SUB(dist, 0.001f);
+        tag = e;
+        return true;
+    }
+    __device__ __forceinline__ void store_closest(int, const HitRec&, bool) const {}
+    __device__ __forceinline__ void store_any(int e, bool occluded) const { W.vis[e] = occluded ? 1 : 0; }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(B2PT_PBLOCK, B2PT_PMINB) k_extend_pool(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr, int P,
+                                                             TraceCounters* __restrict__ tc) {
+    __shared__ PoolSmem<false> sm;
+    IoExtend io{W, list};
+    pool_traverse<false, COUNT>(S, sm, io, &W.totals[4], list ? (long long)*count_ptr : (long long)P, tc);
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(B2PT_PBLOCK, B2PT_PMINB) k_shadow_pool(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
+    __shared__ PoolSmem<true> sm;
+    IoShadow io{W};
+    pool_traverse<true, COUNT>(S, sm, io, &W.totals[5], (long long)W.counters[C_SHADOW], tc);
 }
 
 // Shadow kernel of the ONE statistics batch per scene (occluder-aware child order, build.cu learn_child_order): same
@@ -683,14 +735,22 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 dbg("k_begin_bounce", pix_begin, sb, depth);
                 const int* list = depth == 0 ? nullptr : Wv.q_active[cur];
                 ev();
-                if (fused) {
+                // Shadow rays of the bounces of a scene big enough for a warp's rays to diverge take the phase-split pool
+                // kernel (1M-triangle scene, 32M-path batches: shadow 1276 -> 1167 ms per frame); closest hit stays with the
+                // run-to-completion kernel, which the pool variant does not beat (850 vs 801 ms): B2PT_FLAG_POOL_EXTEND.
+                const bool pooled = !fused && depth > 0 && !(ctx->flags & B2PT_FLAG_LANE_KERNELS);
+                const unsigned pgrid = (unsigned)std::min<long long>(((long long)P + B2PT_PBLOCK * B2PT_PR - 1) / (B2PT_PBLOCK * B2PT_PR), (long long)ctx->sm_count * 8);
+                if (pooled && (ctx->flags & B2PT_FLAG_POOL_EXTEND)) {
+                    if (count) k_extend_pool<true><<<pgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else k_extend_pool<false><<<pgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                } else if (fused) {
                     if (count) k_extend_rtc<true, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                     else k_extend_rtc<false, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 } else {
                     if (count) k_extend_rtc<true, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                     else k_extend_rtc<false, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 }
-                dbg("k_extend_rtc", pix_begin, sb, depth);
+                dbg("k_extend", pix_begin, sb, depth);
                 if (fused) {   // k_extend_rtc has already run the epilogue of its certified rays
                     k_extend_fallback<true><<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
                     dbg("k_extend_fallback", pix_begin, sb, depth);
@@ -707,10 +767,13 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 if (S.nlight > 0) {
                     ++n_shadow;
                     unsigned sg = (unsigned)(((long long)P * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
+                    const unsigned spgrid = (unsigned)std::min<long long>(((long long)P * S.nlight + B2PT_PBLOCK * B2PT_PR - 1) / (B2PT_PBLOCK * B2PT_PR), (long long)ctx->sm_count * 8);
                     if (learn_batch) k_shadow_learn<<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_order_stats, ctx->d_order_stats + 8 * (size_t)S.nwide);
+                    else if (pooled && count) k_shadow_pool<true><<<spgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
+                    else if (pooled) k_shadow_pool<false><<<spgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
                     else if (count) k_shadow_rtc<true><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
                     else k_shadow_rtc<false><<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
-                    dbg("k_shadow_rtc", pix_begin, sb, depth);
+                    dbg("k_shadow", pix_begin, sb, depth);
                 }
                 ev();
                 int nxt = cur ^ 1;

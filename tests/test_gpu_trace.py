@@ -112,7 +112,7 @@ def test_axis_aligned_geometry_reference_quirks(engine):
     assert engine.stats()["shadow_rays"] == len(o2)
 
 
-@pytest.mark.parametrize("flags", [0, pt.FLAG_NO_LEARN_ORDER, pt.FLAG_EXACT_ONLY])
+@pytest.mark.parametrize("flags", [0, pt.FLAG_LANE_KERNELS, pt.FLAG_POOL_EXTEND, pt.FLAG_EXACT_ONLY])
 def test_nonfinite_rays_are_misses(built, flags):
     """NaN / infinite rays (zero or denormal directions normalise to NaN / inf, ray.hpp:12) are misses in the
     reference after a full-tree walk; the kernels answer at once and must not follow EMPTY child slots.  A scene
