@@ -68,11 +68,13 @@ typedef struct b2pt_settings {
     float gamma;
 } b2pt_settings;
 
-/* Which part of the frame this context renders (multi-GPU, one process per GPU).  Pixels are
- * dealt out in tile_size x tile_size tiles, tile k belongs to rank k % tile_world; samples
- * [sample_begin, sample_begin+sample_count) of every owned pixel are traced and the per-pixel sum
- * is divided by settings.samples_per_pixel.  Pixels not owned are written as 0, so the per-rank
- * buffers combine with one sum-reduce.  All-zero struct == whole frame, all samples. */
+/* Which part of the frame this context renders (multi-GPU).  Pixels are dealt out in RUNS of tile_size*tile_size
+ * consecutive pixels in row-major order (run k = pixels [k*A, (k+1)*A), A = tile_size^2 — scanline runs, not 2D tiles);
+ * run k belongs to rank k % tile_world.  Samples [sample_begin, sample_begin+sample_count) of every owned pixel are
+ * traced and the per-pixel sum is divided by settings.samples_per_pixel.  Pixels not owned are written as 0, so the
+ * per-rank buffers combine with one sum-reduce (or a gather).  All-zero struct == whole frame, all samples.
+ * A pass that does not cover all samples never writes the magenta "no valid sample" colour (renderer.hpp:78): that
+ * decision needs the whole sample set (b2pt_progressive_pass makes it on the last pass). */
 typedef struct b2pt_partition {
     int32_t tile_rank;
     int32_t tile_world;   /* 0 or 1 => no tile split */
@@ -147,7 +149,10 @@ int b2pt_trace_closest(b2pt_ctx* ctx, const float* o, const float* d, const floa
 /* Boolean form used for shadow rays (renderer.hpp:274-278). occluded[i] in {0,1}. */
 int b2pt_trace_any(b2pt_ctx* ctx, const float* o, const float* d, const float* tmax, int64_t n,
                    uint8_t* occluded);
-/* Same, all pointers in DEVICE memory of the context's device (d_tmax / d_uv may be NULL). */
+/* Same, all pointers in DEVICE memory of the context's device (d_tmax / d_uv may be NULL).  The context works on its own
+ * non-blocking stream (b2pt_stream): device buffers passed to any *_device entry point must be READY (their producers
+ * finished — synchronise the producing stream first) and must not be in use on other streams until the call returns;
+ * every entry point is synchronous, so results are complete on return. */
 int b2pt_trace_closest_device(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n,
                               int32_t* d_tri, float* d_t, float* d_uv);
 int b2pt_trace_any_device(b2pt_ctx* ctx, const float* d_o, const float* d_d, const float* d_tmax, int64_t n,
@@ -163,9 +168,44 @@ int b2pt_render(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* sett
 int b2pt_render_device(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* settings, uint64_t seed,
                        const b2pt_partition* part, float* d_rgb);
 
-/* Output stage of Renderer::saveImage (src/renderer.cpp:8-17): clamp -> pow(1/gamma) -> truncate to
- * 8 bit, on the device.  d_rgb: n_pixels*3 floats (device); rgb8: n_pixels*3 bytes (host). */
-int b2pt_tonemap(b2pt_ctx* ctx, const float* d_rgb, int64_t n_pixels, float gamma, uint8_t* rgb8);
+/* Progressive, resumable accumulation (generalises the single render call of src/main.cpp:87-92).  _begin fixes camera,
+ * settings and seed and clears the accumulation; every _pass traces the next `sample_count` samples of every pixel
+ * (clamped to what is left of settings.samples_per_pixel), adds them to per-pixel sums that stay on the device and
+ * returns the running mean in rgb (host, may be NULL) and the samples done so far.  Samples are added in sample order,
+ * so after the last pass the frame is BIT-IDENTICAL to one b2pt_render call, whatever the pass sizes.  A b2pt_render /
+ * b2pt_upload_scene in between invalidates the accumulation (call _begin again). */
+int b2pt_progressive_begin(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* settings, uint64_t seed);
+int b2pt_progressive_pass(b2pt_ctx* ctx, int32_t sample_count, float* rgb, int32_t* samples_done);
+
+/* Output stage of Renderer::saveImage (src/renderer.cpp:8-17): clamp -> pow(c, 1/gamma) -> (unsigned char)(c * 255), on
+ * the device and BYTE-EXACT: the byte boundaries are found with the host's own powf (b2pt_tonemap_thresholds) and the
+ * device only compares.  d_rgb: width*height*3 floats (device); rgb8: width*height*3 bytes (host).  flip = 0 keeps the
+ * reference's row order (row 0 = bottom of the view: the reference's PNG is upside down), flip = 1 writes rows top-down. */
+int b2pt_tonemap(b2pt_ctx* ctx, const float* d_rgb, int32_t width, int32_t height, float gamma, int32_t flip, uint8_t* rgb8);
+/* Same for the frame of the last b2pt_render / b2pt_progressive_pass of this context, which stays resident on the
+ * device (what OptixRenderer::saveImage downloads, optix_renderer.cu:459-462). */
+int b2pt_tonemap_last(b2pt_ctx* ctx, float gamma, int32_t flip, uint8_t* rgb8);
+/* thr256[k] = smallest float in [0,1] that the reference's tonemap maps to a byte >= k (host only, no GPU needed). */
+int b2pt_tonemap_thresholds(float gamma, float* thr256);
+
+/* ---- several GPUs behind one renderer object (one process; OptixRenderer is one object too) ----------
+ * The scene is replicated, the frame is split into interleaved runs of 1024 pixels (b2pt_partition, tile_size 32), every
+ * device renders its runs on its own host thread, and device 0 gathers the other devices' runs over NVLink peer loads
+ * (staged copies without peer access).  The frame is bit-identical for every device count. */
+typedef struct b2pt_multi b2pt_multi;
+/* devices: ndev CUDA ordinals (ndev <= 0 or NULL: every visible device; an ordinal may repeat). */
+int b2pt_multi_create(const int32_t* devices, int32_t ndev, int32_t flags, int64_t max_paths_in_flight, b2pt_multi** out);
+void b2pt_multi_destroy(b2pt_multi* m);
+const char* b2pt_multi_last_error(const b2pt_multi* m);   /* m == NULL: last b2pt_multi_create failure */
+int32_t b2pt_multi_device_count(const b2pt_multi* m);
+b2pt_ctx* b2pt_multi_ctx(const b2pt_multi* m, int32_t i);  /* the per-device context (stats, queries) */
+int b2pt_multi_upload_scene(b2pt_multi* m, const float* pos, const float* nrm, const int32_t* mat, int64_t ntri,
+                            const b2pt_material* mats, int32_t nmat, const b2pt_light* lights, int32_t nlight);
+/* rgb: host, width*height*3 floats (may be NULL: the frame stays on device 0 for b2pt_multi_tonemap_last). */
+int b2pt_multi_render(b2pt_multi* m, const b2pt_camera* cam, const b2pt_settings* settings, uint64_t seed, float* rgb);
+int b2pt_multi_tonemap_last(b2pt_multi* m, float gamma, int32_t flip, uint8_t* rgb8);
+/* Counters summed over the devices, times of the slowest device. */
+int b2pt_multi_get_stats(const b2pt_multi* m, b2pt_stats* out);
 
 /* ---- introspection ------------------------------------------------------------------------------ */
 int b2pt_get_stats(const b2pt_ctx* ctx, b2pt_stats* out);

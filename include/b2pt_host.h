@@ -37,6 +37,10 @@ int b2pt_camera_look_at(const float* position, const float* target, const float*
 /* 8-bit RGB PNG, rows in the order given. */
 int b2pt_write_png(const char* path, int32_t width, int32_t height, const uint8_t* rgb8);
 
+/* Linear float framebuffer as a portable float map (.pfm, little-endian RGB); rows in the order given, which for the
+ * reference's frameBuffer (row 0 = bottom of the view) is exactly the PFM convention. */
+int b2pt_write_pfm(const char* path, int32_t width, int32_t height, const float* rgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,8 +63,11 @@ class Stats(C.Structure):
 EXPORTS = [
     "b2pt_create", "b2pt_destroy", "b2pt_last_error", "b2pt_reference_order", "b2pt_upload_scene",
     "b2pt_trace_closest", "b2pt_trace_any", "b2pt_trace_closest_device", "b2pt_trace_any_device",
-    "b2pt_render", "b2pt_render_device", "b2pt_tonemap", "b2pt_get_stats", "b2pt_get_accel_info",
+    "b2pt_render", "b2pt_render_device", "b2pt_tonemap", "b2pt_tonemap_last", "b2pt_tonemap_thresholds",
+    "b2pt_progressive_begin", "b2pt_progressive_pass", "b2pt_get_stats", "b2pt_get_accel_info",
     "b2pt_stream", "b2pt_version",
+    "b2pt_multi_create", "b2pt_multi_destroy", "b2pt_multi_last_error", "b2pt_multi_device_count", "b2pt_multi_ctx",
+    "b2pt_multi_upload_scene", "b2pt_multi_render", "b2pt_multi_tonemap_last", "b2pt_multi_get_stats",
 ]
 
 _lib = None
@@ -97,7 +100,23 @@ def load_library():
     L.b2pt_trace_any_device.argtypes = [vp, vp, vp, vp, i64, vp]
     L.b2pt_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), C.c_uint64, C.POINTER(Partition), vp]
     L.b2pt_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), C.c_uint64, C.POINTER(Partition), vp]
-    L.b2pt_tonemap.argtypes = [vp, vp, i64, C.c_float, vp]
+    L.b2pt_tonemap.argtypes = [vp, vp, i32, i32, C.c_float, i32, vp]
+    L.b2pt_tonemap_last.argtypes = [vp, C.c_float, i32, vp]
+    L.b2pt_tonemap_thresholds.argtypes = [C.c_float, vp]
+    L.b2pt_progressive_begin.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), C.c_uint64]
+    L.b2pt_progressive_pass.argtypes = [vp, i32, vp, C.POINTER(i32)]
+    L.b2pt_multi_create.argtypes = [vp, i32, i32, i64, C.POINTER(vp)]
+    L.b2pt_multi_destroy.argtypes = [vp]
+    L.b2pt_multi_destroy.restype = None
+    L.b2pt_multi_last_error.argtypes = [vp]
+    L.b2pt_multi_last_error.restype = C.c_char_p
+    L.b2pt_multi_device_count.argtypes = [vp]
+    L.b2pt_multi_ctx.argtypes = [vp, i32]
+    L.b2pt_multi_ctx.restype = vp
+    L.b2pt_multi_upload_scene.argtypes = [vp, vp, vp, vp, i64, vp, i32, vp, i32]
+    L.b2pt_multi_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), C.c_uint64, vp]
+    L.b2pt_multi_tonemap_last.argtypes = [vp, C.c_float, i32, vp]
+    L.b2pt_multi_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b2pt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b2pt_get_accel_info.argtypes = [vp, vp]
     L.b2pt_stream.argtypes = [vp]
@@ -151,6 +170,50 @@ REFERENCE_LIGHTS = [   # include/scene.hpp:55-80
 ]
 
 
+def check_scene_arrays(pos, nrm, mat, materials8, lights):
+    """Shapes the C ABI takes on trust: pos/nrm (ntri, 9) float32, mat (ntri,) int32, materials8 (nmat, 8), <= 16 lights.
+    Returns the converted arrays; raises ValueError instead of letting the library read past a short buffer."""
+    pos = _f32(pos)
+    if pos.size % 9:
+        raise ValueError(f"pos has {pos.size} floats: not a whole number of triangles (9 floats each)")
+    pos = pos.reshape(-1, 9)
+    ntri = pos.shape[0]
+    if nrm is not None:
+        nrm = _f32(nrm)
+        if nrm.size != pos.size:
+            raise ValueError(f"nrm has {nrm.size} floats, pos has {pos.size}: one normal per vertex is required")
+        nrm = nrm.reshape(-1, 9)
+    if mat is not None:
+        mat = np.ascontiguousarray(mat, np.int32).reshape(-1)
+        if mat.shape[0] != ntri:
+            raise ValueError(f"mat has {mat.shape[0]} entries for {ntri} triangles")
+    m8 = np.zeros((0, 8), np.float32) if materials8 is None else _f32(materials8)
+    if m8.size % 8:
+        raise ValueError("materials8 must be (nmat, 8): type, r, g, b, roughness, metallic, ior, 0")
+    m8 = m8.reshape(-1, 8)
+    lights = list(lights or [])
+    if len(lights) > 16:
+        raise ValueError(f"{len(lights)} lights: the engine takes at most 16")
+    for l in lights:
+        if len(l) != 3 or len(l[0]) != 3 or len(l[1]) != 3:
+            raise ValueError("a light is ((x, y, z), (r, g, b), intensity)")
+    return pos, nrm, mat, m8, lights
+
+
+def check_ray_arrays(o, d, tmax):
+    """o, d: (n, 3) float32; tmax: (n,) or None."""
+    o, d = _f32(o), _f32(d)
+    if o.size % 3 or d.size != o.size:
+        raise ValueError(f"ray origins ({o.size} floats) and directions ({d.size} floats) must both be (n, 3)")
+    o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+    tm = None
+    if tmax is not None:
+        tm = _f32(tmax).reshape(-1)
+        if tm.shape[0] != o.shape[0]:
+            raise ValueError(f"tmax has {tm.shape[0]} entries for {o.shape[0]} rays")
+    return o, d, tm
+
+
 class Engine:
     """One b2pt context (one GPU)."""
 
@@ -181,17 +244,13 @@ class Engine:
     def upload_scene(self, pos, nrm=None, mat=None, materials8=None, lights=REFERENCE_LIGHTS):
         """pos/nrm: (ntri, 9) in the reference's post-build order; materials8: (nmat, 8) rows of
         (type, r, g, b, roughness, metallic, ior, 0); lights: [(pos3, color3, intensity)]."""
-        pos = _f32(pos).reshape(-1, 9)
+        pos, nrm, mat, m8, lights = check_scene_arrays(pos, nrm, mat, materials8, lights)
         ntri = pos.shape[0]
-        nrm = None if nrm is None else _f32(nrm).reshape(-1, 9)
-        mat = None if mat is None else np.ascontiguousarray(mat, np.int32)
-        m8 = np.zeros((0, 8), np.float32) if materials8 is None else _f32(materials8).reshape(-1, 8)
         mats = (Material * max(len(m8), 1))()
         for i, row in enumerate(m8):
             mats[i].type = int(row[0])
             mats[i].albedo[:] = [float(row[1]), float(row[2]), float(row[3])]
             mats[i].roughness, mats[i].metallic, mats[i].ior = float(row[4]), float(row[5]), float(row[6])
-        lights = list(lights or [])
         ls = (Light * max(len(lights), 1))()
         for i, (p, c, inten) in enumerate(lights):
             ls[i].position[:] = [float(x) for x in p]
@@ -204,10 +263,8 @@ class Engine:
 
     # ---- queries (host buffers)
     def trace_closest(self, o, d, tmax=None, want_uv=True):
-        o = _f32(o).reshape(-1, 3)
-        d = _f32(d).reshape(-1, 3)
+        o, d, tm = check_ray_arrays(o, d, tmax)
         n = o.shape[0]
-        tm = None if tmax is None else _f32(tmax)
         tri = np.empty(n, np.int32)
         t = np.empty(n, np.float32)
         uv = np.empty((n, 2), np.float32) if want_uv else None
@@ -215,10 +272,8 @@ class Engine:
         return tri, t, uv
 
     def trace_any(self, o, d, tmax=None):
-        o = _f32(o).reshape(-1, 3)
-        d = _f32(d).reshape(-1, 3)
+        o, d, tm = check_ray_arrays(o, d, tmax)
         n = o.shape[0]
-        tm = None if tmax is None else _f32(tmax)
         occ = np.empty(n, np.uint8)
         self._check(self._L.b2pt_trace_any(self._h, _p(o), _p(d), _p(tm), n, _p(occ)), "b2pt_trace_any")
         return occ
@@ -260,10 +315,29 @@ class Engine:
         rc = self._L.b2pt_render_device(self._h, C.byref(cam), C.byref(st), seed, None if pt is None else C.byref(pt), d_rgb)
         self._check(rc, "b2pt_render_device")
 
-    def tonemap(self, d_rgb, n_pixels, gamma=2.2):
-        out = np.empty(n_pixels * 3, np.uint8)
-        self._check(self._L.b2pt_tonemap(self._h, d_rgb, n_pixels, gamma, _p(out)), "b2pt_tonemap")
+    def tonemap(self, d_rgb, width, height, gamma=2.2, flip=False):
+        """Device frame -> (H, W, 3) bytes, byte-exact Renderer::saveImage pixel maths (src/renderer.cpp:8-17)."""
+        out = np.empty((height, width, 3), np.uint8)
+        self._check(self._L.b2pt_tonemap(self._h, d_rgb, width, height, gamma, 1 if flip else 0, _p(out)), "b2pt_tonemap")
         return out
+
+    def tonemap_last(self, width, height, gamma=2.2, flip=False):
+        """The frame of the last render() / progressive pass, still resident on the device."""
+        out = np.empty((height, width, 3), np.uint8)
+        self._check(self._L.b2pt_tonemap_last(self._h, gamma, 1 if flip else 0, _p(out)), "b2pt_tonemap_last")
+        return out
+
+    def progressive_begin(self, cam: Camera, width, height, spp, bounces, seed=1234):
+        st = self._settings(width, height, spp, bounces)
+        self._check(self._L.b2pt_progressive_begin(self._h, C.byref(cam), C.byref(st), seed), "b2pt_progressive_begin")
+        self._prog_shape = (height, width, 3)
+
+    def progressive_pass(self, sample_count, want_frame=True):
+        """Traces the next `sample_count` samples per pixel; returns (samples_done, running-mean frame or None)."""
+        fb = np.empty(self._prog_shape, np.float32) if want_frame else None
+        done = C.c_int32(0)
+        self._check(self._L.b2pt_progressive_pass(self._h, sample_count, _p(fb), C.byref(done)), "b2pt_progressive_pass")
+        return int(done.value), fb
 
     # ---- introspection
     def stats(self) -> dict:
@@ -280,3 +354,72 @@ class Engine:
     @property
     def stream(self) -> int:
         return int(self._L.b2pt_stream(self._h) or 0)
+
+
+def tonemap_thresholds(gamma: float) -> np.ndarray:
+    """thr[k] = smallest float the reference's tonemap maps to a byte >= k (host only)."""
+    out = np.empty(256, np.float32)
+    if load_library().b2pt_tonemap_thresholds(gamma, _p(out)) != 0:
+        raise B2ptError("b2pt_tonemap_thresholds failed")
+    return out
+
+
+class MultiEngine:
+    """Several GPUs behind one renderer object, one process (include/b2pt.h, b2pt_multi_*)."""
+
+    def __init__(self, devices=None, flags: int = 0, max_paths: int = 0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        devs = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        rc = self._L.b2pt_multi_create(_p(devs), 0 if devs is None else len(devs), flags, max_paths, C.byref(self._h))
+        if rc != 0:
+            raise B2ptError(f"b2pt_multi_create failed ({rc}): {self._L.b2pt_multi_last_error(None).decode()}")
+        self.ndev = int(self._L.b2pt_multi_device_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.b2pt_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise B2ptError(f"{what} failed ({rc}): {self._L.b2pt_multi_last_error(self._h).decode()}")
+
+    def upload_scene(self, pos, nrm=None, mat=None, materials8=None, lights=REFERENCE_LIGHTS):
+        pos, nrm, mat, m8, lights = check_scene_arrays(pos, nrm, mat, materials8, lights)
+        mats = (Material * max(len(m8), 1))()
+        for i, row in enumerate(m8):
+            mats[i].type = int(row[0])
+            mats[i].albedo[:] = [float(row[1]), float(row[2]), float(row[3])]
+            mats[i].roughness, mats[i].metallic, mats[i].ior = float(row[4]), float(row[5]), float(row[6])
+        ls = (Light * max(len(lights), 1))()
+        for i, (p, c, inten) in enumerate(lights):
+            ls[i].position[:] = [float(x) for x in p]
+            ls[i].color[:] = [float(x) for x in c]
+            ls[i].intensity = float(inten)
+        self._check(self._L.b2pt_multi_upload_scene(self._h, _p(pos), _p(nrm), _p(mat), pos.shape[0], C.cast(mats, C.c_void_p), len(m8),
+                                                    C.cast(ls, C.c_void_p), len(lights)), "b2pt_multi_upload_scene")
+
+    def render(self, cam: Camera, width, height, spp, bounces, seed=1234, out=None):
+        if out is not None and (out.shape != (height, width, 3) or out.dtype != np.float32 or not out.flags.c_contiguous):
+            out = None
+        fb = np.empty((height, width, 3), np.float32) if out is None else out
+        st = Settings(width, height, spp, bounces, 2.2)
+        self._check(self._L.b2pt_multi_render(self._h, C.byref(cam), C.byref(st), seed, _p(fb)), "b2pt_multi_render")
+        return fb
+
+    def tonemap_last(self, width, height, gamma=2.2, flip=False):
+        out = np.empty((height, width, 3), np.uint8)
+        self._check(self._L.b2pt_multi_tonemap_last(self._h, gamma, 1 if flip else 0, _p(out)), "b2pt_multi_tonemap_last")
+        return out
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._L.b2pt_multi_get_stats(self._h, C.byref(s)), "b2pt_multi_get_stats")
+        return s.as_dict()

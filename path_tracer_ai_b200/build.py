@@ -18,7 +18,7 @@ HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "libb2pt.so")
 CLI = os.path.join(HERE, "b2pt_cli")
 
-CU_SOURCES = ["api.cu", "build.cu", "trace.cu", "render.cu"]
+CU_SOURCES = ["api.cu", "build.cu", "trace.cu", "render.cu", "multi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

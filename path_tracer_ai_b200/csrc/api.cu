@@ -283,16 +283,71 @@ int b2pt_render(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* sett
     int rc = scratch_reserve(ctx, 7, bytes, &d_rgb);
     if (rc) return rc;
     if ((rc = b2pt_render_device(ctx, cam, settings, seed, part, (float*)d_rgb))) return rc;
+    ctx->last_width = settings->width; ctx->last_height = settings->height;
     B2PT_CUDA(ctx, cudaMemcpyAsync(rgb, d_rgb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     B2PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B2PT_OK;
 }
 
-int b2pt_tonemap(b2pt_ctx* ctx, const float* d_rgb, int64_t n_pixels, float gamma, uint8_t* rgb8) {
-    if (!ctx) return B2PT_ERR_INVALID;
-    if (!d_rgb || !rgb8 || n_pixels < 0) { ctx->err = "b2pt_tonemap: bad arguments"; return B2PT_ERR_INVALID; }
+// ---- progressive rendering ---------------------------------------------------------------------------------------------
+int b2pt_progressive_begin(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* settings, uint64_t seed) {
+    int rc = require_scene(ctx, "b2pt_progressive_begin");
+    if (rc) return rc;
+    if (!cam || !settings) { ctx->err = "b2pt_progressive_begin: NULL argument"; return B2PT_ERR_INVALID; }
+    if (settings->width < 2 || settings->height < 2 || settings->samples_per_pixel < 1 || settings->max_bounces < 0) {
+        ctx->err = "b2pt_progressive_begin: width/height must be >= 2, samples >= 1, bounces >= 0";
+        return B2PT_ERR_INVALID;
+    }
+    ctx->prog_active = true; ctx->prog_cam = *cam; ctx->prog_settings = *settings; ctx->prog_seed = seed; ctx->prog_done = 0;
+    return B2PT_OK;
+}
+
+int b2pt_progressive_pass(b2pt_ctx* ctx, int32_t sample_count, float* rgb, int32_t* samples_done) {
+    int rc = require_scene(ctx, "b2pt_progressive_pass");
+    if (rc) return rc;
+    if (!ctx->prog_active) { ctx->err = "b2pt_progressive_pass: call b2pt_progressive_begin first"; return B2PT_ERR_INVALID; }
+    const b2pt_settings& st = ctx->prog_settings;
+    const int left = st.samples_per_pixel - ctx->prog_done;
+    if (sample_count <= 0 || left <= 0) { ctx->err = "b2pt_progressive_pass: no samples left (or sample_count <= 0)"; return B2PT_ERR_INVALID; }
+    const int n = std::min<int>(sample_count, left);
     B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
-    return tonemap_frame(ctx, d_rgb, n_pixels, gamma, rgb8);
+    size_t bytes = sizeof(float) * 3ull * (size_t)st.width * (size_t)st.height;
+    void* d_rgb = nullptr;
+    if ((rc = scratch_reserve(ctx, 7, bytes, &d_rgb))) return rc;
+    b2pt_partition part{};
+    part.sample_begin = ctx->prog_done; part.sample_count = n;
+    begin_call(ctx);
+    // the per-pixel sums stay on the device between passes; the estimate is the running mean
+    if ((rc = render_frame(ctx, &ctx->prog_cam, &st, ctx->prog_seed, &part, (float*)d_rgb, ctx->prog_done > 0, ctx->prog_done + n))) { ctx->prog_active = false; return rc; }
+    if ((rc = end_call(ctx))) return rc;
+    ctx->prog_done += n;
+    ctx->last_width = st.width; ctx->last_height = st.height;
+    if (samples_done) *samples_done = ctx->prog_done;
+    if (rgb) {
+        B2PT_CUDA(ctx, cudaMemcpyAsync(rgb, d_rgb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        B2PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return B2PT_OK;
+}
+
+int b2pt_tonemap(b2pt_ctx* ctx, const float* d_rgb, int32_t width, int32_t height, float gamma, int32_t flip, uint8_t* rgb8) {
+    if (!ctx) return B2PT_ERR_INVALID;
+    if (!d_rgb || !rgb8 || width < 0 || height < 0) { ctx->err = "b2pt_tonemap: bad arguments"; return B2PT_ERR_INVALID; }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    return tonemap_frame(ctx, d_rgb, width, height, gamma, flip, rgb8);
+}
+
+int b2pt_tonemap_last(b2pt_ctx* ctx, float gamma, int32_t flip, uint8_t* rgb8) {
+    if (!ctx) return B2PT_ERR_INVALID;
+    if (!rgb8) { ctx->err = "b2pt_tonemap_last: NULL output"; return B2PT_ERR_INVALID; }
+    if (ctx->last_width <= 0 || !ctx->scratch[7]) { ctx->err = "b2pt_tonemap_last: nothing rendered yet"; return B2PT_ERR_INVALID; }
+    B2PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    return tonemap_frame(ctx, (const float*)ctx->scratch[7], ctx->last_width, ctx->last_height, gamma, flip, rgb8);
+}
+
+int b2pt_tonemap_thresholds(float gamma, float* thr256) {
+    if (!thr256 || !(gamma > 0.0f)) return B2PT_ERR_INVALID;
+    return tonemap_thresholds(gamma, thr256);
 }
 
 int b2pt_get_stats(const b2pt_ctx* ctx, b2pt_stats* out) {

@@ -108,6 +108,17 @@ struct b2pt_ctx {
     int* d_fallback_count = nullptr;
     b2pt_stats stats{};
     int64_t accel_info[8] = {};
+    // output stage: byte thresholds of the last gamma used (render.cu tonemap_thresholds)
+    float tonemap_gamma = 0.0f;
+    float tonemap_thr[256] = {};
+    // the frame of the last b2pt_render / progressive pass stays on the device (scratch slot 7) for b2pt_tonemap_frame
+    int last_width = 0, last_height = 0;
+    // progressive rendering (b2pt_progressive_begin / _pass)
+    bool prog_active = false;
+    b2pt_camera prog_cam{};
+    b2pt_settings prog_settings{};
+    uint64_t prog_seed = 0;
+    int prog_done = 0;
 };
 
 namespace b2pt {
@@ -140,7 +151,8 @@ int launch_trace_any(b2pt_ctx* ctx, const float* d_o, const float* d_d, const fl
 
 // render.cu
 int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st, uint64_t seed,
-                 const b2pt_partition* part, float* d_rgb);
-int tonemap_frame(b2pt_ctx* ctx, const float* d_rgb, int64_t npix, float gamma, uint8_t* rgb8_host);
+                 const b2pt_partition* part, float* d_rgb, bool keep_accum = false, int divisor = 0);
+int tonemap_thresholds(float gamma, float* thr256);
+int tonemap_frame(b2pt_ctx* ctx, const float* d_rgb, int width, int height, float gamma, int flip, uint8_t* rgb8_host);
 
 }  // namespace b2pt

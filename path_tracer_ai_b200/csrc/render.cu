@@ -22,6 +22,7 @@
 // (scene, camera, settings, seed), independent of chunking, queue order and GPU count.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <cstdlib>
 
 #include "traverse_pool.cuh"
@@ -579,14 +580,14 @@ __global__ void __launch_bounds__(256) k_resolve(Wave W, float4* __restrict__ ac
 }
 
 // renderer.hpp:75-81
-__global__ void __launch_bounds__(256) k_finalize(const float4* __restrict__ accum, FrameConst F, long long nown, int all_samples, float* __restrict__ rgb) {
+__global__ void __launch_bounds__(256) k_finalize(const float4* __restrict__ accum, FrameConst F, long long nown, int all_samples, int divisor, float* __restrict__ rgb) {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nown) return;
     long long i = pixel_of(F, j);
     float4 a = accum[j];
     float r, g, b;
     if (a.w != 0.0f) {
-        float spp = (float)F.spp_total;
+        float spp = (float)divisor;
         r = B2PT_DIV(a.x, spp); g = B2PT_DIV(a.y, spp); b = B2PT_DIV(a.z, spp);
     } else if (all_samples) {
         r = 1.0f; g = 0.0f; b = 1.0f;   // debug colour for pixels without a valid sample (:78)
@@ -596,20 +597,42 @@ __global__ void __launch_bounds__(256) k_finalize(const float4* __restrict__ acc
     rgb[3 * i + 0] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
 }
 
-// Renderer::saveImage's tonemap (src/renderer.cpp:8-17): clamp, pow(1/gamma), truncate.
-__global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ rgb, long long n, float inv_gamma, uint8_t* __restrict__ out) {
+// Renderer::saveImage's tonemap (src/renderer.cpp:8-17): clamp -> pow(c, 1/gamma) -> (unsigned char)(c * 255).  The byte a
+// value maps to is decided by the HOST's libm powf, the function the reference calls: tonemap_frame finds, for every byte
+// value k, the smallest float whose reference byte is >= k (a bisection over float bit patterns with the host's own powf)
+// and the device only compares against those 255 thresholds — byte-exact without a device pow.  `flip` writes the rows
+// top-down (the reference's image is upside down: renderer.hpp:81 stores row 0 = bottom of the view).
+__global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ rgb, int width, int height, int flip, const float* __restrict__ thr,
+                                                  uint8_t* __restrict__ out) {
+    __shared__ float s_thr[256];
+    s_thr[threadIdx.x] = thr[threadIdx.x];
+    __syncthreads();
+    const long long n = 3ll * width * height;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float c = rgb[i];
-    c = gmin(gmax(c, 0.0f), 1.0f);
-    c = powf(c, inv_gamma);
-    out[i] = (uint8_t)(c * 255.0f);
+    c = gmin(gmax(c, 0.0f), 1.0f);          // glm::clamp = min(max(x, lo), hi); a NaN stays a NaN and maps to byte 0
+    int lo = 0, hi = 255;                   // largest k with thr[k] <= c  (thr[0] = 0, thr non-decreasing)
+#pragma unroll
+    for (int step = 0; step < 8; ++step) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_thr[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    long long o = i;
+    if (flip) {
+        const long long row = i / (3ll * width), col = i - row * 3ll * width;
+        o = (height - 1 - row) * 3ll * width + col;
+    }
+    out[o] = (uint8_t)lo;
 }
 
 }  // namespace
 
+// keep_accum: the per-pixel sums of the previous call stay (progressive rendering: the samples of successive passes are
+// added in sample order, exactly as one call over the whole range would add them); divisor: what the sums are divided
+// by (0 = settings.samples_per_pixel).
 int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st, uint64_t seed,
-                 const b2pt_partition* part, float* d_rgb) {
+                 const b2pt_partition* part, float* d_rgb, bool keep_accum, int divisor) {
     cudaStream_t stream = ctx->stream;
     const DeviceScene& S = ctx->scene;
     const int W_ = st->width, H_ = st->height;
@@ -625,7 +648,8 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     int s_begin = part ? part->sample_begin : 0;
     int s_count = (part && part->sample_count > 0) ? part->sample_count : st->samples_per_pixel - s_begin;
     if (s_begin < 0 || s_count < 0 || s_begin + s_count > st->samples_per_pixel) { ctx->err = "b2pt_render: sample range out of bounds"; return B2PT_ERR_INVALID; }
-    const int all_samples = (s_begin == 0 && s_count == st->samples_per_pixel) ? 1 : 0;
+    const int all_samples = ((s_begin == 0 || keep_accum) && s_begin + s_count == st->samples_per_pixel) ? 1 : 0;
+    if (divisor <= 0) divisor = st->samples_per_pixel;
 
     // owned pixels: runs of tile_area consecutive pixels (row-major), run k -> rank k % world
     long long nown = npix;
@@ -689,7 +713,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     Wv.counters = (int*)cnt;
     Wv.totals = (unsigned long long*)((char*)cnt + 128);
     B2PT_CUDA(ctx, cudaMemsetAsync(cnt, 0, 256, stream));
-    B2PT_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(float4) * (size_t)nown, stream));
+    if (!keep_accum) B2PT_CUDA(ctx, cudaMemsetAsync(accum, 0, sizeof(float4) * (size_t)nown, stream));
 
     const bool count = (ctx->flags & B2PT_FLAG_COUNT_FETCHES) != 0;
     // closest-hit kernel with the per-vertex epilogue fused in: small trees only (see k_extend_rtc)
@@ -785,7 +809,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
             dbg("k_resolve", pix_begin, sb, -1);
         }
     }
-    k_finalize<<<(unsigned)((nown + 255) / 256), 256, 0, stream>>>((const float4*)accum, F, nown, all_samples, d_rgb);
+    k_finalize<<<(unsigned)((nown + 255) / 256), 256, 0, stream>>>((const float4*)accum, F, nown, all_samples, divisor, d_rgb);
     ++launches;
     cudaError_t le = cudaGetLastError();
     unsigned long long totals[3] = {0, 0, 0};
@@ -812,12 +836,52 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     return B2PT_OK;
 }
 
-int tonemap_frame(b2pt_ctx* ctx, const float* d_rgb, int64_t npix, float gamma, uint8_t* rgb8_host) {
-    void* d_out = nullptr;
-    int rc = scratch_reserve(ctx, 11, (size_t)npix * 3, &d_out);
+namespace {
+// (unsigned char)(powf(clamp(c), 1/gamma) * 255) on the host, as src/renderer.cpp:11-16 computes it
+inline int reference_byte(float c, float inv_gamma) {
+    c = c < 0.0f ? 0.0f : c; c = 1.0f < c ? 1.0f : c;
+    return (int)(unsigned char)(std::pow(c, inv_gamma) * 255.0f);
+}
+}  // namespace
+
+// thr[k] = smallest float in [0, 1] whose reference byte is >= k (thr[0] = 0).  powf is monotone in practice; the
+// neighbourhood of every threshold is re-checked and a violation refuses the device path (the caller tonemaps on the host).
+int tonemap_thresholds(float gamma, float* thr) {
+    const float inv = 1.0f / gamma;
+    thr[0] = 0.0f;
+    const int top = reference_byte(1.0f, inv);
+    for (int k = 1; k < 256; ++k) {
+        if (k > top) { thr[k] = __builtin_inff(); continue; }
+        uint32_t lo = 0u, hi = 0x3f800000u;   // bit patterns of 0.0f .. 1.0f: ordered like the floats
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo) / 2;
+            float x; std::memcpy(&x, &mid, 4);
+            if (reference_byte(x, inv) >= k) hi = mid; else lo = mid + 1;
+        }
+        std::memcpy(&thr[k], &lo, 4);
+        for (int d = -48; d <= 48; ++d) {   // monotone around the threshold?
+            int64_t b = (int64_t)lo + d;
+            if (b < 0 || b > 0x3f800000) continue;
+            uint32_t ub = (uint32_t)b; float x; std::memcpy(&x, &ub, 4);
+            if ((reference_byte(x, inv) >= k) != (d >= 0)) return B2PT_ERR_INVALID;
+        }
+    }
+    return B2PT_OK;
+}
+
+int tonemap_frame(b2pt_ctx* ctx, const float* d_rgb, int width, int height, float gamma, int flip, uint8_t* rgb8_host) {
+    if (!(gamma > 0.0f)) { ctx->err = "b2pt_tonemap: gamma must be positive"; return B2PT_ERR_INVALID; }
+    const long long n = 3ll * width * height;
+    void *d_out = nullptr, *d_thr = nullptr;
+    int rc = scratch_reserve(ctx, 11, (size_t)std::max<long long>(n, 1), &d_out);
     if (rc) return rc;
-    long long n = npix * 3;
-    if (n > 0) k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_rgb, n, 1.0f / gamma, (uint8_t*)d_out);
+    if ((rc = scratch_reserve(ctx, 12, 256 * sizeof(float), &d_thr))) return rc;
+    if (ctx->tonemap_gamma != gamma) {
+        if (tonemap_thresholds(gamma, ctx->tonemap_thr)) { ctx->err = "b2pt_tonemap: host powf is not monotone around a byte threshold for this gamma"; return B2PT_ERR_INVALID; }
+        ctx->tonemap_gamma = gamma;
+    }
+    B2PT_CUDA(ctx, cudaMemcpyAsync(d_thr, ctx->tonemap_thr, 256 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_rgb, width, height, flip, (const float*)d_thr, (uint8_t*)d_out);
     B2PT_CUDA(ctx, cudaGetLastError());
     B2PT_CUDA(ctx, cudaMemcpyAsync(rgb8_host, d_out, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     B2PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

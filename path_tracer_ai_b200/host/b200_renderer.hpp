@@ -2,9 +2,13 @@
 // same nested Settings (same defaults), same lifecycle — ctor, initialize(), uploadScene(const Scene&),
 // render(const Camera&), saveImage(const std::string&) — and the same error convention (every failure
 // throws std::runtime_error with the failing call's text).  Thin C++ over the C ABI in include/b2pt.h.
+//
+// Beyond the reference's surface: a list of devices (one object, one process, N GPUs: b2pt_multi_*),
+// renderProgressive (resumable accumulation), saveImage's `flip` (the reference writes its PNG upside down; flip
+// writes it upright) and a .pfm float dump when the file name ends in ".pfm".
 #pragma once
-#include <cmath>
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -28,15 +32,28 @@ public:
     };
 
     explicit B200Renderer(const Settings& settings = Settings(), int device = 0, uint64_t seed = 1234)
-        : settings(settings), device(device), seed(seed) {}
-    ~B200Renderer() { if (ctx) b2pt_destroy(ctx); }
+        : settings(settings), devices(1, device), seed(seed) {}
+    // several GPUs of one box behind the same object (scene replicated, interleaved pixel runs, gather on devices[0])
+    B200Renderer(const Settings& settings, const std::vector<int>& devices, uint64_t seed = 1234)
+        : settings(settings), devices(devices), seed(seed) {}
+    ~B200Renderer() {
+        if (multi) b2pt_multi_destroy(multi);
+        else if (ctx) b2pt_destroy(ctx);
+    }
     B200Renderer(const B200Renderer&) = delete;
     B200Renderer& operator=(const B200Renderer&) = delete;
 
     void initialize() {
-        b2pt_config cfg{};
-        cfg.device = device;
-        if (b2pt_create(&cfg, &ctx) != B2PT_OK) throw std::runtime_error(b2pt_last_error(nullptr));
+        if (devices.size() > 1) {
+            std::vector<int32_t> d(devices.begin(), devices.end());
+            if (b2pt_multi_create(d.data(), static_cast<int32_t>(d.size()), 0, 0, &multi) != B2PT_OK)
+                throw std::runtime_error(b2pt_multi_last_error(nullptr));
+            ctx = b2pt_multi_ctx(multi, 0);
+        } else {
+            b2pt_config cfg{};
+            cfg.device = devices.empty() ? 0 : devices[0];
+            if (b2pt_create(&cfg, &ctx) != B2PT_OK) throw std::runtime_error(b2pt_last_error(nullptr));
+        }
     }
 
     void uploadScene(const Scene& scene) {
@@ -70,49 +87,83 @@ public:
             c.intensity = l.intensity;
             ls.push_back(c);
         }
-        check(b2pt_upload_scene(ctx, pos.data(), nrm.data(), mat.data(), static_cast<int64_t>(n), mats.data(),
-                                static_cast<int32_t>(mats.size()), ls.data(), static_cast<int32_t>(ls.size())));
+        if (multi)
+            checkMulti(b2pt_multi_upload_scene(multi, pos.data(), nrm.data(), mat.data(), static_cast<int64_t>(n), mats.data(),
+                                               static_cast<int32_t>(mats.size()), ls.data(), static_cast<int32_t>(ls.size())));
+        else
+            check(b2pt_upload_scene(ctx, pos.data(), nrm.data(), mat.data(), static_cast<int64_t>(n), mats.data(),
+                                    static_cast<int32_t>(mats.size()), ls.data(), static_cast<int32_t>(ls.size())));
     }
 
     void render(const Camera& camera) {
         requireInit("render");   // optix_renderer.cu:421-423
         b2pt_camera cam = camera.toC();
-        b2pt_settings st{settings.width, settings.height, settings.samplesPerPixel, settings.maxBounces, settings.gamma};
+        b2pt_settings st = cSettings();
         frame.assign(static_cast<size_t>(settings.width) * settings.height * 3, 0.0f);
-        check(b2pt_render(ctx, &cam, &st, seed, nullptr, frame.data()));
+        if (multi) checkMulti(b2pt_multi_render(multi, &cam, &st, seed, frame.data()));
+        else check(b2pt_render(ctx, &cam, &st, seed, nullptr, frame.data()));
     }
 
-    // Renderer::saveImage (src/renderer.cpp:5-21): clamp, pow(1/gamma), truncate to 8 bit, PNG with
-    // rows in framebuffer order (row 0 = bottom of the view — the reference writes it that way too).
-    void saveImage(const std::string& filename) {
-        if (frame.empty()) throw std::runtime_error("saveImage: nothing rendered yet");
-        std::vector<uint8_t> px(frame.size());
-        const float inv = 1.0f / settings.gamma;
-        for (size_t i = 0; i < frame.size(); ++i) {
-            float c = clamp1(frame[i], 0.0f, 1.0f);
-            c = std::pow(c, inv);
-            px[i] = static_cast<uint8_t>(c * 255.0f);
+    // Progressive, resumable accumulation: passes of `samplesPerPass` samples per pixel until settings.samplesPerPixel
+    // are done; `onPass(samplesDone, frame)` sees the running mean after every pass (return false to stop early).  The
+    // last frame is bit-identical to render().  Single device.
+    void renderProgressive(const Camera& camera, int samplesPerPass, const std::function<bool(int, const std::vector<float>&)>& onPass = nullptr) {
+        requireInit("renderProgressive");
+        if (multi) throw std::runtime_error("renderProgressive: one device only");
+        b2pt_camera cam = camera.toC();
+        b2pt_settings st = cSettings();
+        frame.assign(static_cast<size_t>(settings.width) * settings.height * 3, 0.0f);
+        check(b2pt_progressive_begin(ctx, &cam, &st, seed));
+        int32_t done = 0;
+        while (done < settings.samplesPerPixel) {
+            check(b2pt_progressive_pass(ctx, samplesPerPass, frame.data(), &done));
+            if (onPass && !onPass(done, frame)) break;
         }
+    }
+
+    // Renderer::saveImage (src/renderer.cpp:5-21): clamp, pow(1/gamma), truncate to 8 bit — on the GPU, byte-exact
+    // (b2pt_tonemap_last) — PNG with rows in framebuffer order (row 0 = bottom of the view: the reference writes it
+    // that way too) unless `flip`.  A name ending in ".pfm" writes the linear float frame instead.
+    void saveImage(const std::string& filename, bool flip = false) {
+        if (frame.empty()) throw std::runtime_error("saveImage: nothing rendered yet");
+        if (filename.size() >= 4 && filename.compare(filename.size() - 4, 4, ".pfm") == 0) {
+            if (!writePfmRGB(filename, settings.width, settings.height, frame.data())) throw std::runtime_error("saveImage: cannot write " + filename);
+            return;
+        }
+        std::vector<uint8_t> px(frame.size());
+        if (multi) checkMulti(b2pt_multi_tonemap_last(multi, settings.gamma, flip ? 1 : 0, px.data()));
+        else check(b2pt_tonemap_last(ctx, settings.gamma, flip ? 1 : 0, px.data()));
         if (!writePngRGB8(filename, settings.width, settings.height, px.data()))
             throw std::runtime_error("saveImage: cannot write " + filename);
     }
 
     const std::vector<float>& frameBuffer() const { return frame; }
-    b2pt_stats stats() const { b2pt_stats s{}; if (ctx) b2pt_get_stats(ctx, &s); return s; }
+    b2pt_stats stats() const {
+        b2pt_stats s{};
+        if (multi) b2pt_multi_get_stats(multi, &s);
+        else if (ctx) b2pt_get_stats(ctx, &s);
+        return s;
+    }
     b2pt_ctx* handle() const { return ctx; }
+    int deviceCount() const { return multi ? b2pt_multi_device_count(multi) : 1; }
 
 private:
+    b2pt_settings cSettings() const { return b2pt_settings{settings.width, settings.height, settings.samplesPerPixel, settings.maxBounces, settings.gamma}; }
     void requireInit(const char* who) const {
         if (!ctx) throw std::runtime_error(std::string("B200Renderer::") + who + " called before initialize()");
     }
     void check(int rc) const {
         if (rc != B2PT_OK) throw std::runtime_error(b2pt_last_error(ctx));
     }
+    void checkMulti(int rc) const {
+        if (rc != B2PT_OK) throw std::runtime_error(b2pt_multi_last_error(multi));
+    }
 
     Settings settings;
-    int device;
+    std::vector<int> devices;
     uint64_t seed;
     b2pt_ctx* ctx = nullptr;
+    b2pt_multi* multi = nullptr;
     std::vector<float> frame;
 };
 

@@ -105,4 +105,9 @@ int b2pt_write_png(const char* path, int32_t width, int32_t height, const uint8_
     return b2pt::writePngRGB8(path, width, height, rgb8) ? B2PT_OK : B2PT_ERR_INVALID;
 }
 
+int b2pt_write_pfm(const char* path, int32_t width, int32_t height, const float* rgb) {
+    if (!path || !rgb || width <= 0 || height <= 0) return B2PT_ERR_INVALID;
+    return b2pt::writePfmRGB(path, width, height, rgb) ? B2PT_OK : B2PT_ERR_INVALID;
+}
+
 }  // extern "C"

@@ -3,7 +3,9 @@
 //   -m/--mode {cpu,gpu} (gpu)  -w/--width (800)  -h/--height (450; note: -h is height, not help)
 //   -s/--samples (100)  -b/--bounces (5)  -g/--gamma (2.2)  -i/--input (IronMan/IronMan.obj)
 //   -o/--output (output.png)  --help
-// Extras: --seed N (default 1234), --device N, --dump-float FILE (raw float32 W*H*3 framebuffer),
+// Extras: --seed N (default 1234), --device N, --gpus N (devices 0..N-1 behind the one renderer object), --flip (write the
+// image upright: the reference's PNG is upside down), --progressive N (N samples per pass, resumable accumulation),
+// an --output ending in .pfm (linear float frame), --dump-float FILE (raw float32 W*H*3 framebuffer),
 // --camera-pos x,y,z / --camera-target x,y,z / --fov deg (defaults = the constants of src/main.cpp:46-51),
 // --lights x,y,z,r,g,b,I[;...] (default = the four constants of include/scene.hpp:55-80).
 // Same flow as src/main.cpp:39-96: Scene -> loadFromObj -> fixed Camera -> renderer -> saveImage,
@@ -38,6 +40,9 @@ const Opt kOpts[] = {
     {"output", 'o', true, "output.png", "Output image file path"},
     {"seed", 0, true, "1234", "RNG seed (Philox key)"},
     {"device", 0, true, "0", "CUDA device ordinal"},
+    {"gpus", 0, true, "1", "Render on devices 0..N-1 (scene replicated, interleaved pixel runs, one gather per frame)"},
+    {"flip", 0, false, "", "Write the image upright (the reference writes it upside down)"},
+    {"progressive", 0, true, "0", "Accumulate in passes of N samples per pixel (0 = one pass)"},
     {"dump-float", 0, true, "", "Also write the float framebuffer (raw float32, W*H*3)"},
     {"camera-pos", 0, true, "0,2,5", "Camera position x,y,z (reference: fixed at 0,2,5)"},
     {"camera-target", 0, true, "0,1.8,0", "Camera target x,y,z (reference: fixed at 0,1.8,0)"},
@@ -143,22 +148,36 @@ int main(int argc, char* argv[]) {
         settings.maxBounces = std::atoi(args["bounces"].c_str());
         settings.gamma = static_cast<float>(std::atof(args["gamma"].c_str()));
 
-        b2pt::B200Renderer renderer(settings, std::atoi(args["device"].c_str()), std::strtoull(args["seed"].c_str(), nullptr, 10));
+        const int gpus = std::atoi(args["gpus"].c_str());
+        if (gpus < 1 || gpus > 16) throw std::runtime_error("Option 'gpus' must be between 1 and 16");
+        std::vector<int> devices;
+        if (gpus == 1) devices.push_back(std::atoi(args["device"].c_str()));
+        else for (int d = 0; d < gpus; ++d) devices.push_back(d);
+        const uint64_t seed = std::strtoull(args["seed"].c_str(), nullptr, 10);
+        b2pt::B200Renderer renderer(settings, devices, seed);
         renderer.initialize();
+        const int perPass = std::atoi(args["progressive"].c_str());
 
         auto t0 = std::chrono::high_resolution_clock::now();
         renderer.uploadScene(scene);
-        renderer.render(camera);
+        if (perPass > 0) {
+            renderer.renderProgressive(camera, perPass, [&](int done, const std::vector<float>&) {
+                std::cout << "\rsamples per pixel: " << done << " / " << settings.samplesPerPixel << std::flush;
+                return true;
+            });
+        } else {
+            renderer.render(camera);
+        }
         auto t1 = std::chrono::high_resolution_clock::now();
         double secs = std::chrono::duration<double>(t1 - t0).count();
         b2pt_stats s = renderer.stats();
         std::cout << "\nRendering completed in " << secs << " seconds" << std::endl;
-        std::printf("{\"samples\": %lld, \"extend_rays\": %lld, \"shadow_rays\": %lld, \"fallback_rays\": %lld, \"gpu_seconds\": %.6f, "
+        std::printf("{\"gpus\": %d, \"samples\": %lld, \"extend_rays\": %lld, \"shadow_rays\": %lld, \"fallback_rays\": %lld, \"gpu_seconds\": %.6f, "
                     "\"msamples_per_s\": %.3f, \"mrays_per_s\": %.3f}\n",
-                    (long long)s.samples, (long long)s.extend_rays, (long long)s.shadow_rays, (long long)s.fallback_rays, s.gpu_seconds,
+                    renderer.deviceCount(), (long long)s.samples, (long long)s.extend_rays, (long long)s.shadow_rays, (long long)s.fallback_rays, s.gpu_seconds,
                     s.samples / s.gpu_seconds * 1e-6, (s.extend_rays + s.shadow_rays) / s.gpu_seconds * 1e-6);
 
-        renderer.saveImage(outputFile);
+        renderer.saveImage(outputFile, args.count("flip") != 0);
         if (!args["dump-float"].empty()) {
             FILE* f = std::fopen(args["dump-float"].c_str(), "wb");
             if (!f) { std::cerr << "Error: cannot write " << args["dump-float"] << std::endl; return -1; }

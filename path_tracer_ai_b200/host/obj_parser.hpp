@@ -86,6 +86,26 @@ inline bool fix_index(int raw, int count, int* out) {
     return false;  // 0 is not a valid OBJ index
 }
 
+// Out-of-range references would make the caller index past the arrays.  A face that names a vertex that does not
+// exist fails the load; a normal / texture coordinate that does not exist is treated as absent (-1), with a warning.
+template <class MeshT>
+inline bool validate_indices(MeshT& mesh) {
+    const int nv = static_cast<int>(mesh.vertices.size() / 3);
+    const int nn = static_cast<int>(mesh.normals.size() / 3);
+    const int nt = static_cast<int>(mesh.texcoords.size() / 2);
+    bool warned = false;
+    for (auto& i : mesh.indices) {
+        if (i.vertex_index < 0 || i.vertex_index >= nv) {
+            mesh.error = "Face references a vertex that does not exist\n";
+            return false;
+        }
+        if (i.normal_index >= nn || i.normal_index < -1) { i.normal_index = -1; warned = true; }
+        if (i.texcoord_index >= nt || i.texcoord_index < -1) { i.texcoord_index = -1; warned = true; }
+    }
+    if (warned) mesh.warning += "Face references a normal or texture coordinate that does not exist (ignored)\n";
+    return true;
+}
+
 inline std::string dirname_of(const std::string& path) {
     size_t pos = path.find_last_of("/\\");
     return pos == std::string::npos ? std::string() : path.substr(0, pos + 1);
@@ -225,12 +245,12 @@ inline void parse_chunk(Chunk& c) {
                     ++p;
                     if (*p != '/') {
                         long ti = std::strtol(p, &end, 10);
-                        if (end != p) { fix_index(static_cast<int>(ti), nt, &idx.texcoord_index); p = end; }
+                        if (end != p) { if (!fix_index(static_cast<int>(ti), nt, &idx.texcoord_index)) idx.texcoord_index = -1; p = end; }
                     }
                     if (*p == '/') {
                         ++p;
                         long ni = std::strtol(p, &end, 10);
-                        if (end != p) { fix_index(static_cast<int>(ni), nn, &idx.normal_index); p = end; }
+                        if (end != p) { if (!fix_index(static_cast<int>(ni), nn, &idx.normal_index)) idx.normal_index = -1; p = end; }
                     }
                 }
                 poly.push_back(idx);
@@ -350,15 +370,7 @@ inline bool parse_file(const std::string& path, Mesh& mesh, int nthreads = 0, si
         for (int fe : c.face_event) mesh.material_ids.push_back(fe < 0 ? carry_in : ev_mat[fe]);
         c = Chunk{};   // release the chunk's memory
     }
-    // Out-of-range vertex references would make the caller index past the arrays; report them.
-    const int nv = static_cast<int>(mesh.vertices.size() / 3);
-    for (const Index& i : mesh.indices) {
-        if (i.vertex_index < 0 || i.vertex_index >= nv) {
-            mesh.error = "Face references a vertex that does not exist\n";
-            return false;
-        }
-    }
-    return true;
+    return detail::validate_indices(mesh);
 }
 
 // The same parser reading line by line on one thread (kept as the statement the chunked parser is tested against).
@@ -409,12 +421,12 @@ inline bool parse_file_serial(const std::string& path, Mesh& mesh) {
                     ++p;
                     if (*p != '/') {
                         long ti = std::strtol(p, &end, 10);
-                        if (end != p) { fix_index(static_cast<int>(ti), nt, &idx.texcoord_index); p = end; }
+                        if (end != p) { if (!fix_index(static_cast<int>(ti), nt, &idx.texcoord_index)) idx.texcoord_index = -1; p = end; }
                     }
                     if (*p == '/') {
                         ++p;
                         long ni = std::strtol(p, &end, 10);
-                        if (end != p) { fix_index(static_cast<int>(ni), nn, &idx.normal_index); p = end; }
+                        if (end != p) { if (!fix_index(static_cast<int>(ni), nn, &idx.normal_index)) idx.normal_index = -1; p = end; }
                     }
                 }
                 poly.push_back(idx);
@@ -447,15 +459,7 @@ inline bool parse_file_serial(const std::string& path, Mesh& mesh) {
         // g / o / s / anything else: ignored
     }
     std::fclose(f);
-    // Out-of-range vertex references would make the caller index past the arrays; report them.
-    const int nv = static_cast<int>(mesh.vertices.size() / 3);
-    for (const Index& i : mesh.indices) {
-        if (i.vertex_index < 0 || i.vertex_index >= nv) {
-            mesh.error = "Face references a vertex that does not exist\n";
-            return false;
-        }
-    }
-    return true;
+    return detail::validate_indices(mesh);
 }
 
 }  // namespace obj

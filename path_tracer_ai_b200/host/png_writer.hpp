@@ -48,4 +48,16 @@ inline bool writePngRGB8(const std::string& path, int width, int height, const u
     return std::fclose(f) == 0;
 }
 
+// Portable float map ("PF", little-endian, 3 channels): the linear float framebuffer without tone mapping.  A PFM stores
+// its rows bottom-to-top, which is the order of the reference's frameBuffer (renderer.hpp:81: row 0 = bottom of the view),
+// so the buffer is written as it is and any PFM viewer shows the image upright.
+inline bool writePfmRGB(const std::string& path, int width, int height, const float* rgb) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    std::fprintf(f, "PF\n%d %d\n-1.0\n", width, height);
+    const size_t n = (size_t)width * height * 3;
+    bool ok = std::fwrite(rgb, sizeof(float), n, f) == n;
+    return (std::fclose(f) == 0) && ok;
+}
+
 }  // namespace b2pt

@@ -44,6 +44,7 @@ def _host_lib():
         L.b2pt_scene_get_lights.argtypes = [vp, vp]
         L.b2pt_camera_look_at.argtypes = [vp, vp, vp, C.c_float, C.POINTER(_capi.Camera)]
         L.b2pt_write_png.argtypes = [C.c_char_p, C.c_int32, C.c_int32, vp]
+        L.b2pt_write_pfm.argtypes = [C.c_char_p, C.c_int32, C.c_int32, vp]
         L.b2pt_obj_parser_selfcheck.argtypes = [C.c_char_p, C.c_int32, C.c_int64]
         L.b2pt_obj_parser_selfcheck.restype = C.c_int
         L._host_ready = True
@@ -52,7 +53,7 @@ def _host_lib():
 
 HOST_EXPORTS = ["b2pt_scene_load_obj", "b2pt_scene_free", "b2pt_scene_num_triangles", "b2pt_scene_num_materials",
                 "b2pt_scene_num_lights", "b2pt_scene_get_triangles", "b2pt_scene_get_materials", "b2pt_scene_get_lights",
-                "b2pt_camera_look_at", "b2pt_write_png", "b2pt_obj_parser_selfcheck"]
+                "b2pt_camera_look_at", "b2pt_write_png", "b2pt_write_pfm", "b2pt_obj_parser_selfcheck"]
 
 
 class Camera:
@@ -112,13 +113,13 @@ class Scene:
 
     def setContents(self, pos, nrm, mat, materials8):
         """Triangles in arbitrary order -> applies the reference BVH::build ordering (bvh.hpp:27-72)."""
-        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 9)
+        pos, nrm, mat, m8, _ = _capi.check_scene_arrays(pos, nrm, mat, materials8, self.lights)   # ValueError on mismatched lengths
         order = _capi.reference_order(pos)
         self.order = order
         self.pos = pos[order]
-        self.nrm = (np.zeros_like(pos) if nrm is None else np.ascontiguousarray(nrm, np.float32).reshape(-1, 9))[order]
-        self.mat = (np.zeros(len(pos), np.int32) if mat is None else np.ascontiguousarray(mat, np.int32))[order]
-        self.materials8 = np.ascontiguousarray(materials8, np.float32).reshape(-1, 8)
+        self.nrm = (np.zeros_like(pos) if nrm is None else nrm)[order]
+        self.mat = (np.zeros(len(pos), np.int32) if mat is None else mat)[order]
+        self.materials8 = m8
 
     def getTriangles(self): return self.pos, self.nrm, self.mat
     def getMaterials(self): return self.materials8
@@ -126,67 +127,85 @@ class Scene:
 
 
 class B200Renderer:
-    """Drop-in for OptixRenderer: initialize / uploadScene / render / saveImage."""
+    """Drop-in for OptixRenderer: initialize / uploadScene / render / saveImage.  `devices=[...]` puts several GPUs of
+    one box behind the same object (b2pt_multi_*: scene replicated, interleaved pixel runs, one gather per frame)."""
 
-    def __init__(self, settings: Settings | None = None, device: int = 0, seed: int = 1234, flags: int = 0, max_paths: int = 0):
+    def __init__(self, settings: Settings | None = None, device: int = 0, seed: int = 1234, flags: int = 0, max_paths: int = 0,
+                 devices=None):
         self.settings = settings or Settings()
         self.device, self.seed, self.flags, self.max_paths = device, seed, flags, max_paths
+        self.devices = None if devices is None else list(devices)
         self.engine: Engine | None = None
+        self.multi: _capi.MultiEngine | None = None
         self.frameBuffer: np.ndarray | None = None
 
     def initialize(self):
-        self.engine = Engine(self.device, self.flags, self.max_paths)
+        if self.devices is not None and len(self.devices) > 1:
+            self.multi = _capi.MultiEngine(self.devices, self.flags, self.max_paths)
+        else:
+            self.engine = Engine(self.device if self.devices is None else self.devices[0], self.flags, self.max_paths)
 
     def _require(self, who):
-        if self.engine is None:
+        if self.engine is None and self.multi is None:
             raise B2ptError(f"B200Renderer.{who} called before initialize()")   # optix_renderer.cu:421-423
 
     def uploadScene(self, scene: Scene):
         self._require("uploadScene")
-        self.engine.upload_scene(scene.pos, scene.nrm, scene.mat, scene.materials8, scene.lights)
+        (self.multi or self.engine).upload_scene(scene.pos, scene.nrm, scene.mat, scene.materials8, scene.lights)
 
     def render(self, camera: Camera, part=None):
         self._require("render")
         s = self.settings
         # like the reference's frameBuffer member, the array is reused by the next render() of this renderer
-        self.frameBuffer = self.engine.render(camera.c, s.width, s.height, s.samplesPerPixel, s.maxBounces, self.seed, part,
-                                              out=self.frameBuffer)
+        if self.multi is not None:
+            if part is not None:
+                raise B2ptError("render: a multi-device renderer partitions the frame itself")
+            self.frameBuffer = self.multi.render(camera.c, s.width, s.height, s.samplesPerPixel, s.maxBounces, self.seed, out=self.frameBuffer)
+        else:
+            self.frameBuffer = self.engine.render(camera.c, s.width, s.height, s.samplesPerPixel, s.maxBounces, self.seed, part,
+                                                  out=self.frameBuffer)
         return self.frameBuffer
 
     def renderProgressive(self, camera: Camera, samples_per_pass: int):
-        """Progressive, resumable accumulation: yields (samples_done, estimate) after every pass of
-        `samples_per_pass` samples per pixel.  Pass k renders the sample range [k*n, (k+1)*n) of the frame through
-        `b2pt_partition.sample_begin/sample_count`, so the union of the passes is exactly the sample set of the
-        one-shot frame (same Philox streams); only the order of the float additions differs.  The estimate after a
-        pass is the running mean; the last one equals render() up to that rounding."""
+        """Progressive, resumable accumulation through b2pt_progressive_begin / _pass: yields
+        (samples_done, estimate) after every pass of `samples_per_pass` samples per pixel.  The per-pixel sums stay on
+        the device and samples are added in sample order, so the LAST estimate is bit-identical to render(); the
+        magenta "no valid sample" colour (renderer.hpp:78) is decided on the last pass only."""
         self._require("renderProgressive")
+        if self.engine is None:
+            raise B2ptError("renderProgressive: one device only")
         s = self.settings
-        total = s.samplesPerPixel
-        accum = np.zeros((s.height, s.width, 3), np.float64)
+        self.engine.progressive_begin(camera.c, s.width, s.height, s.samplesPerPixel, s.maxBounces, self.seed)
         done = 0
-        while done < total:
-            n = min(samples_per_pass, total - done)
-            part = self.engine.render(camera.c, s.width, s.height, total, s.maxBounces, self.seed,
-                                      dict(sample_begin=done, sample_count=n))
-            accum += part.astype(np.float64) * total     # a pass returns (sum of its samples) / total
-            done += n
-            self.frameBuffer = (accum / done).astype(np.float32)
-            yield done, self.frameBuffer
+        while done < s.samplesPerPixel:
+            done, fb = self.engine.progressive_pass(samples_per_pass)
+            self.frameBuffer = fb
+            yield done, fb
 
-    def tonemapped(self) -> np.ndarray:
-        """Renderer::saveImage's pixel maths (src/renderer.cpp:8-17) on the host: clamp, pow(1/gamma), truncate."""
+    def tonemapped(self, flip: bool = False) -> np.ndarray:
+        """Renderer::saveImage's pixel maths (src/renderer.cpp:8-17) — clamp, pow(1/gamma), truncate — on the GPU,
+        byte-exact, from the frame the last render left on the device."""
         if self.frameBuffer is None:
             raise B2ptError("saveImage: nothing rendered yet")
-        c = np.clip(self.frameBuffer, 0.0, 1.0).astype(np.float32)
-        c = np.power(c, np.float32(1.0 / self.settings.gamma), dtype=np.float32)
-        return (c * np.float32(255.0)).astype(np.uint8)
+        s = self.settings
+        return (self.multi or self.engine).tonemap_last(s.width, s.height, s.gamma, flip)
 
-    def saveImage(self, filename: str):
-        px = np.ascontiguousarray(self.tonemapped())
+    def saveImage(self, filename: str, flip: bool = False):
+        """PNG (rows in framebuffer order like the reference, upright with flip=True), or the linear float frame when
+        the name ends in .pfm."""
         L = _host_lib()
-        if L.b2pt_write_png(os.fsencode(filename), self.settings.width, self.settings.height, px.ctypes.data) != 0:
+        s = self.settings
+        if filename.lower().endswith(".pfm"):
+            if self.frameBuffer is None:
+                raise B2ptError("saveImage: nothing rendered yet")
+            fb = np.ascontiguousarray(self.frameBuffer, np.float32)
+            if L.b2pt_write_pfm(os.fsencode(filename), s.width, s.height, fb.ctypes.data) != 0:
+                raise B2ptError(f"saveImage: cannot write {filename}")
+            return
+        px = np.ascontiguousarray(self.tonemapped(flip))
+        if L.b2pt_write_png(os.fsencode(filename), s.width, s.height, px.ctypes.data) != 0:
             raise B2ptError(f"saveImage: cannot write {filename}")
 
     def stats(self):
         self._require("stats")
-        return self.engine.stats()
+        return (self.multi or self.engine).stats()

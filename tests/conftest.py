@@ -47,3 +47,21 @@ def prebuild_from_scene(sc):
 
 def cam13_of(cam):
     return np.concatenate([cam.getPosition(), cam.getForward(), cam.getRight(), cam.getUp(), [cam.getFOV()]]).astype(np.float32)
+
+
+def reference_tonemap(fb, gamma):
+    """Renderer::saveImage's pixel maths (reference src/renderer.cpp:8-17) with the function the reference calls:
+    glm::pow(float) is std::pow(float, float), i.e. libm's powf (numpy's float32 power is a different implementation
+    and differs from it in the last bit for ~18 % of inputs).  clamp -> powf(c, 1/gamma) -> (unsigned char)(c * 255)."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.powf.restype = ctypes.c_float
+    libm.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    v = np.ascontiguousarray(fb, np.float32)
+    inv = float(np.float32(1.0) / np.float32(gamma))
+    flat = np.clip(v.reshape(-1), 0, 1)
+    out = np.empty(flat.shape[0], np.uint8)
+    for i, x in enumerate(flat):
+        c = np.float32(libm.powf(float(x), inv)) * np.float32(255.0)
+        out[i] = int(c) if np.isfinite(c) else 0
+    return out.reshape(v.shape)

@@ -9,7 +9,7 @@ import path_tracer_ai_b200 as pt
 from oracle import PortOracle
 from path_tracer_ai_b200 import scenes
 
-from conftest import bits, cam13_of, prebuild_from_scene
+from conftest import bits, cam13_of, prebuild_from_scene, reference_tonemap
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -167,7 +167,10 @@ def test_converged_render_matches_reference_golden(engine):
     assert abs(lum(fb).mean() / lum(ref).mean() - 1) < 0.005
 
 
-def test_tonemap_matches_host(engine, cornell):
+def test_tonemap_is_byte_exact(engine, cornell):
+    """The GPU output stage (threshold table built with the host's powf) reproduces Renderer::saveImage's pixel maths
+    (src/renderer.cpp:8-17) byte for byte — on a rendered frame, on every float around every byte boundary, and on
+    the special values; flip only reverses the rows."""
     import torch
     sc = cornell
     engine.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
@@ -175,30 +178,76 @@ def test_tonemap_matches_host(engine, cornell):
     d_rgb = torch.empty(W * H * 3, dtype=torch.float32, device="cuda:0")
     torch.cuda.synchronize()
     engine.render_device(pt.Camera().c, W, H, 4, 3, d_rgb.data_ptr(), seed=3)
+
+    host = reference_tonemap   # libm powf, the function the reference's glm::pow ends in
+
     fb = d_rgb.cpu().numpy().reshape(H, W, 3)
-    px = engine.tonemap(d_rgb.data_ptr(), W * H, 2.2).reshape(H, W, 3)
-    host = (np.power(np.clip(fb, 0, 1), np.float32(1 / 2.2), dtype=np.float32) * np.float32(255)).astype(np.uint8)
-    assert np.abs(px.astype(int) - host.astype(int)).max() <= 1     # device powf vs libm pow: at most 1 LSB
-    assert (px != host).mean() < 0.01
+    for gamma in (2.2, 1.0, 2.4, 0.7):
+        px = engine.tonemap(d_rgb.data_ptr(), W, H, gamma)
+        assert np.array_equal(px, host(fb, gamma)), gamma
+        assert np.array_equal(engine.tonemap(d_rgb.data_ptr(), W, H, gamma, flip=True), px[::-1])
+    # a synthetic frame: 64 floats either side of every byte threshold, plus specials
+    from path_tracer_ai_b200 import _capi
+    thr = _capi.tonemap_thresholds(2.2)
+    vals = []
+    for k in range(1, 256):
+        b = int(thr[k:k + 1].view(np.uint32)[0])
+        vals.append(np.arange(max(b - 64, 0), min(b + 64, 0x3f800000) + 1, dtype=np.uint32).view(np.float32))
+    vals.append(np.float32([0.0, -0.0, 1.0, 2.5, -3.0, 1e-30, 1e-45, np.inf, -np.inf, 0.5, 0.18]))
+    v = np.concatenate(vals)
+    pad = (-len(v)) % 3
+    v = np.concatenate([v, np.zeros(pad, np.float32)])
+    t = torch.from_numpy(v).cuda()
+    torch.cuda.synchronize()
+    px = engine.tonemap(t.data_ptr(), len(v) // 3, 1, 2.2).reshape(-1)
+    assert np.array_equal(px, host(v, 2.2))
 
 
-def test_progressive_accumulation_converges_to_the_one_shot_frame(built, cornell):
-    """Passes over disjoint sample ranges add up to the one-shot frame (same Philox streams, different float
-    addition order), and every intermediate estimate is the frame a renderer with that many samples of the SAME
-    streams would average."""
+def test_progressive_accumulation_is_bit_identical_to_the_one_shot_frame(built, cornell):
+    """b2pt_progressive_pass adds the samples of successive passes to per-pixel sums on the device in sample order:
+    whatever the pass sizes, the last frame equals render() bit for bit, and every intermediate estimate is the frame
+    a one-shot render of that many samples gives."""
     r = pt.B200Renderer(pt.Settings(width=96, height=54, samplesPerPixel=24, maxBounces=4), seed=77)
     r.initialize()
     r.uploadScene(cornell)
     cam = pt.Camera()
     full = r.render(cam).copy()
-    seen = []
-    for done, est in r.renderProgressive(cam, 7):
-        seen.append(done)
-        assert est.shape == full.shape and np.isfinite(est).all()
-    assert seen == [7, 14, 21, 24]
-    assert np.allclose(r.frameBuffer, full, rtol=2e-5, atol=1e-7)
+    for per_pass in (7, 1, 24, 100):
+        seen, frames = [], []
+        for done, est in r.renderProgressive(cam, per_pass):
+            seen.append(done)
+            frames.append(est.copy())
+        assert seen[-1] == 24 and seen == sorted(seen)
+        assert np.array_equal(bits(frames[-1]), bits(full)), per_pass
+    # the estimate after 7 of 24 samples is the 7-spp frame of the same streams (sum / 7)
+    r7 = pt.B200Renderer(pt.Settings(width=96, height=54, samplesPerPixel=7, maxBounces=4), seed=77)
+    r7.initialize(); r7.uploadScene(cornell)
     first = next(iter(r.renderProgressive(cam, 7)))[1]
-    assert not np.allclose(first, full, rtol=1e-3)        # 7 samples are not 24
+    assert np.array_equal(bits(first), bits(r7.render(cam)))
+    # the PNG of a progressive render is the PNG of the one-shot render
+    list(r.renderProgressive(cam, 5))
+    assert np.array_equal(r.tonemapped(), reference_tonemap(r.frameBuffer, 2.2))
+
+
+def test_multi_device_renderer_is_bit_identical(built, cornell):
+    """b2pt_multi_*: one object, N contexts (here N contexts on the devices that exist — an ordinal may repeat, which
+    exercises partition + gather on a single GPU too).  Frame and PNG bytes equal the single-device renderer's."""
+    import torch
+    st = pt.Settings(width=200, height=120, samplesPerPixel=6, maxBounces=4)
+    one = pt.B200Renderer(st, seed=5)
+    one.initialize(); one.uploadScene(cornell)
+    ref = one.render(pt.Camera()).copy()
+    ref_px = one.tonemapped()
+    ndev = torch.cuda.device_count()
+    for devices in ([0, 0], [0, 0, 0], list(range(ndev)) if ndev > 1 else [0, 0, 0, 0, 0]):
+        m = pt.B200Renderer(st, seed=5, devices=devices)
+        m.initialize(); m.uploadScene(cornell)
+        fb = m.render(pt.Camera())
+        assert np.array_equal(bits(fb), bits(ref)), devices
+        assert np.array_equal(m.tonemapped(), ref_px)
+        s = m.stats()
+        assert s["samples"] == 200 * 120 * 6
+        m.multi.close()
 
 
 def test_b200renderer_lifecycle_and_png(built, cornell, tmp_path):
@@ -224,6 +273,27 @@ def test_b200renderer_lifecycle_and_png(built, cornell, tmp_path):
     cfb = np.fromfile(dump, np.float32).reshape(36, 64, 3)
     assert np.array_equal(bits(cfb), bits(fb))
     assert (tmp_path / "c.png").read_bytes() == data
+    assert np.array_equal(r.tonemapped(), reference_tonemap(fb, 2.2))     # GPU output stage == the reference's host maths
+    # --gpus (contexts 0..N-1 behind one renderer), --progressive and --flip / .pfm outputs
+    import torch
+    n = min(torch.cuda.device_count(), 2)
+    res = subprocess.run([cli, "-i", obj, "-w", "64", "-h", "36", "-s", "4", "-b", "3", "-o", str(tmp_path / "g.png"), "--gpus", str(n)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert (tmp_path / "g.png").read_bytes() == data
+    res = subprocess.run([cli, "-i", obj, "-w", "64", "-h", "36", "-s", "4", "-b", "3", "-o", str(tmp_path / "p.png"), "--progressive", "3"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert (tmp_path / "p.png").read_bytes() == data
+    res = subprocess.run([cli, "-i", obj, "-w", "64", "-h", "36", "-s", "4", "-b", "3", "-o", str(tmp_path / "f.pfm")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    raw = (tmp_path / "f.pfm").read_bytes()
+    assert raw.startswith(b"PF\n64 36\n-1.0\n")
+    assert np.array_equal(bits(np.frombuffer(raw[len(b"PF\n64 36\n-1.0\n"):], np.float32).reshape(36, 64, 3)), bits(fb))
+    r.saveImage(str(tmp_path / "up.png"), flip=True)
+    res = subprocess.run([cli, "-i", obj, "-w", "64", "-h", "36", "-s", "4", "-b", "3", "-o", str(tmp_path / "cf.png"), "--flip"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert (tmp_path / "cf.png").read_bytes() == (tmp_path / "up.png").read_bytes() != data
     # camera / light / seed overrides of the CLI reach the engine exactly like the Python arguments do
     lights = [((1.0, 3.0, 1.5), (1.0, 0.8, 0.6), 7.5), ((-2.0, 1.0, 2.0), (0.3, 0.5, 1.0), 4.0)]
     res = subprocess.run([cli, "-i", obj, "-w", "64", "-h", "36", "-s", "4", "-b", "3", "-o", str(tmp_path / "d.png"),

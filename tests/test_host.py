@@ -13,7 +13,7 @@ import path_tracer_ai_b200 as pt
 from oracle import PortOracle, RefOracle
 from path_tracer_ai_b200 import scenes
 
-from conftest import bits
+from conftest import bits, reference_tonemap
 
 needs_ref = pytest.mark.skipif(not (oracle.ref_available() or os.path.isdir("/root/reference/include")),
                                reason="oracle/_ref not built and /root/reference absent")
@@ -134,6 +134,67 @@ def test_chunked_obj_parser_equals_line_by_line(built, tmp_path):
     assert L.b2pt_obj_parser_selfcheck(os.fsencode(str(tmp_path / "missing.obj")), 2, 64) < 0
     (tmp_path / "empty.obj").write_bytes(b"")
     assert L.b2pt_obj_parser_selfcheck(os.fsencode(str(tmp_path / "empty.obj")), 4, 1) == 0
+
+
+def test_obj_out_of_range_normal_and_texcoord_indices(built, tmp_path):
+    """An OBJ whose faces name normals / texture coordinates that do not exist must not crash the loader: those
+    references are treated as absent (the loader then uses the face normal), a missing VERTEX fails the load."""
+    p = tmp_path / "bad.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\n"
+                 "f 1//300000000 2//300000000 3//300000000\n"     # normals far out of range
+                 "f 1/77/1 2/77/1 3/77/1\n"                        # texcoords out of range, normals fine
+                 "f 1//-5 2//-5 3//-5\n")                          # negative index reaching before the first normal
+    sc = pt.Scene()
+    assert sc.loadFromObj(str(p))
+    assert len(sc.pos) == 8 + 3
+    assert np.isfinite(sc.nrm).all()
+    (tmp_path / "bad2.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n")
+    assert not pt.Scene().loadFromObj(str(tmp_path / "bad2.obj"))
+    # both parsers agree on the malformed file
+    L = pt.load_library()
+    from path_tracer_ai_b200 import renderer
+    renderer._host_lib()
+    assert L.b2pt_obj_parser_selfcheck(str(p).encode(), 4, 7) == 0
+
+
+def test_python_binding_rejects_mismatched_array_lengths(built):
+    """The C ABI takes array lengths on trust; the binding must raise instead of letting it read past a short buffer."""
+    from path_tracer_ai_b200 import _capi
+    pos = np.zeros((4, 9), np.float32)
+    with pytest.raises(ValueError):
+        _capi.check_scene_arrays(pos, np.zeros((3, 9), np.float32), None, None, [])
+    with pytest.raises(ValueError):
+        _capi.check_scene_arrays(pos, None, np.zeros(5, np.int32), None, [])
+    with pytest.raises(ValueError):
+        _capi.check_scene_arrays(np.zeros(10, np.float32), None, None, None, [])
+    with pytest.raises(ValueError):
+        _capi.check_scene_arrays(pos, None, None, None, [((0, 0, 0), (1, 1, 1), 1.0)] * 17)
+    with pytest.raises(ValueError):
+        _capi.check_ray_arrays(np.zeros((5, 3)), np.zeros((4, 3)), None)
+    with pytest.raises(ValueError):
+        _capi.check_ray_arrays(np.zeros((5, 3)), np.zeros((5, 3)), np.zeros(4))
+    with pytest.raises(ValueError):
+        pt.Scene().setContents(pos, np.zeros((3, 9), np.float32), None, np.zeros((1, 8), np.float32))
+    o, d, tm = _capi.check_ray_arrays(np.zeros((5, 3)), np.ones((5, 3)), np.ones(5))
+    assert o.dtype == np.float32 and tm.shape == (5,)
+
+
+@pytest.mark.parametrize("gamma", [2.2, 1.0, 2.4, 0.45])
+def test_tonemap_thresholds_split_the_floats_like_the_reference_maths(built, gamma):
+    """b2pt_tonemap_thresholds (host powf bisection): thr[k] is the first float whose reference byte is >= k."""
+    from path_tracer_ai_b200 import _capi
+    thr = _capi.tonemap_thresholds(gamma)
+
+    def host(v):
+        return reference_tonemap(v, gamma).astype(int)
+
+    assert thr[0] == 0.0 and (np.diff(thr) >= 0).all()
+    at = host(thr)
+    below = host(np.maximum(thr.view(np.uint32).astype(np.int64) - 1, 0).astype(np.uint32).view(np.float32))
+    for k in range(1, 256):
+        assert at[k] >= k and below[k] < k, k
+    x = np.random.default_rng(1).random(20000).astype(np.float32)
+    assert np.array_equal(np.searchsorted(thr, x, side="right") - 1, host(x))
 
 
 def test_camera_matches_oracle(built):
