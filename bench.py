@@ -57,7 +57,7 @@ WORKLOADS = {
 }
 DEFAULT_MAX_PATHS = 32 << 20
 TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_traffic.json")
-KERNEL_SOURCES = ["exact.cuh", "ctx.cuh", "traverse.cuh", "traverse_rtc.cuh", "traverse_thread.cuh", "render.cu", "trace.cu", "build.cu"]
+KERNEL_SOURCES = ["exact.cuh", "ctx.cuh", "traverse.cuh", "traverse_rtc.cuh", "traverse_thread.cuh", "traverse_pool.cuh", "render.cu", "trace.cu", "build.cu"]
 
 
 def kernel_source_hash() -> str:
@@ -502,7 +502,8 @@ def main():
     nodes_per_ray = cst["node_fetches"] / max(nrays_c, 1)
     tris_per_ray = cst["tri_fetches"] / max(nrays_c, 1)
     shadow_dominant = agg["shadow_seconds"] >= agg["extend_seconds"]
-    dominant = "k_shadow_rtc" if shadow_dominant else "k_extend_rtc"
+    # shadow rays: k_shadow_rtc at depth 0 (coherent), k_shadow_pool on the bounces; closest hit: k_extend_rtc
+    dominant = "k_shadow_pool" if shadow_dominant else "k_extend_rtc"
     if shadow_dominant:
         # per shadow ray: read the queue entry (4 B) and the vertex it shares with the other lights
         # (g0+g1 = 32 B / nlight), write the visibility byte

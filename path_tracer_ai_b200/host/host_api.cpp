@@ -23,6 +23,14 @@ int b2pt_scene_load_obj(const char* path, b2pt_scene** out) {
     return B2PT_OK;
 }
 
+int b2pt_scene_load_obj_cached(const char* path, const char* cache_path, b2pt_scene** out) {
+    if (!path || !out) return B2PT_ERR_INVALID;
+    b2pt_scene* s = new b2pt_scene();
+    if (!s->scene.loadFromObjCached(path, cache_path ? cache_path : "")) { delete s; *out = nullptr; return B2PT_ERR_INVALID; }
+    *out = s;
+    return B2PT_OK;
+}
+
 void b2pt_scene_free(b2pt_scene* s) { delete s; }
 
 int b2pt_obj_parser_selfcheck(const char* path, int32_t nthreads, int64_t chunk_bytes) {

@@ -5,7 +5,7 @@
 //   -o/--output (output.png)  --help
 // Extras: --seed N (default 1234), --device N, --gpus N (devices 0..N-1 behind the one renderer object), --flip (write the
 // image upright: the reference's PNG is upside down), --progressive N (N samples per pass, resumable accumulation),
-// an --output ending in .pfm (linear float frame), --dump-float FILE (raw float32 W*H*3 framebuffer),
+// an --output ending in .pfm (linear float frame), --cache (binary scene cache next to the OBJ), --dump-float FILE (raw float32 W*H*3 framebuffer),
 // --camera-pos x,y,z / --camera-target x,y,z / --fov deg (defaults = the constants of src/main.cpp:46-51),
 // --lights x,y,z,r,g,b,I[;...] (default = the four constants of include/scene.hpp:55-80).
 // Same flow as src/main.cpp:39-96: Scene -> loadFromObj -> fixed Camera -> renderer -> saveImage,
@@ -42,6 +42,7 @@ const Opt kOpts[] = {
     {"device", 0, true, "0", "CUDA device ordinal"},
     {"gpus", 0, true, "1", "Render on devices 0..N-1 (scene replicated, interleaved pixel runs, one gather per frame)"},
     {"flip", 0, false, "", "Write the image upright (the reference writes it upside down)"},
+    {"cache", 0, false, "", "Reuse / write the binary scene cache <input>.b2ptscene (skips OBJ parsing and BVH::build ordering)"},
     {"progressive", 0, true, "0", "Accumulate in passes of N samples per pixel (0 = one pass)"},
     {"dump-float", 0, true, "", "Also write the float framebuffer (raw float32, W*H*3)"},
     {"camera-pos", 0, true, "0,2,5", "Camera position x,y,z (reference: fixed at 0,2,5)"},
@@ -109,7 +110,7 @@ int main(int argc, char* argv[]) {
 
         b2pt::Scene scene;
         std::cout << "Loading model from: " << inputFile << std::endl;
-        if (!scene.loadFromObj(inputFile)) {
+        if (!(args.count("cache") ? scene.loadFromObjCached(inputFile) : scene.loadFromObj(inputFile))) {
             std::cerr << "Failed to load model: " << inputFile << std::endl;   // main.cpp:40-43
             return -1;
         }

@@ -7,10 +7,12 @@
 // intersector: Scene::intersect (scene.hpp:96-99) is served by the GPU engine through
 // B200Renderer / b2pt_trace_closest, and there is no CPU fallback.
 #pragma once
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <sys/stat.h>
 #include <algorithm>
 #include <string>
 #include <thread>
@@ -122,6 +124,84 @@ public:
         triangles = std::move(tris);
         materials = std::move(mats);
         applyReferenceOrder();
+    }
+
+    // ---- binary scene cache ------------------------------------------------------------------------------------
+    // Parsing a 10M-triangle OBJ and putting it into the reference's BVH::build order (std::nth_element per node,
+    // bvh.hpp:63-66) takes seconds on the host; the result depends only on the files.  saveCache writes the finished
+    // scene (triangles in post-build order, build order, materials, lights); loadFromObjCached reuses it while the
+    // OBJ's size and modification time are the ones recorded in it, and rebuilds + rewrites it otherwise.
+    bool saveCache(const std::string& cachePath, const std::string& objPath = std::string()) const {
+        static_assert(sizeof(Triangle) == 100, "Triangle is written as it is");
+        FILE* f = std::fopen(cachePath.c_str(), "wb");
+        if (!f) return false;
+        struct stat sb{};
+        const bool have = !objPath.empty() && ::stat(objPath.c_str(), &sb) == 0;
+        const uint64_t hdr[8] = {0x314e435354503242ull /* "B2PTSCN1" */, static_cast<uint64_t>(triangles.size()), static_cast<uint64_t>(materials.size()),
+                                 static_cast<uint64_t>(lights.size()), have ? static_cast<uint64_t>(sb.st_size) : 0ull,
+                                 have ? static_cast<uint64_t>(sb.st_mtim.tv_sec) : 0ull, have ? static_cast<uint64_t>(sb.st_mtim.tv_nsec) : 0ull, sizeof(Triangle)};
+        bool ok = std::fwrite(hdr, sizeof(hdr), 1, f) == 1;
+        if (!triangles.empty()) ok = ok && std::fwrite(triangles.data(), sizeof(Triangle), triangles.size(), f) == triangles.size();
+        if (!buildOrder.empty()) ok = ok && std::fwrite(buildOrder.data(), sizeof(int), buildOrder.size(), f) == buildOrder.size();
+        for (const auto& m : materials) {
+            const float rec[8] = {static_cast<float>(static_cast<int>(m->type)), m->albedo.x, m->albedo.y, m->albedo.z, m->roughness, m->metallic, m->ior, 0.0f};
+            ok = ok && std::fwrite(rec, sizeof(rec), 1, f) == 1;
+        }
+        for (const auto& l : lights) {
+            const float rec[7] = {l.position.x, l.position.y, l.position.z, l.color.x, l.color.y, l.color.z, l.intensity};
+            ok = ok && std::fwrite(rec, sizeof(rec), 1, f) == 1;
+        }
+        return (std::fclose(f) == 0) && ok;
+    }
+
+    // objPath non-empty: the cache is only accepted if it was written for that file as it is now.
+    bool loadCache(const std::string& cachePath, const std::string& objPath = std::string()) {
+        FILE* f = std::fopen(cachePath.c_str(), "rb");
+        if (!f) return false;
+        uint64_t hdr[8] = {};
+        bool ok = std::fread(hdr, sizeof(hdr), 1, f) == 1 && hdr[0] == 0x314e435354503242ull && hdr[7] == sizeof(Triangle) &&
+                  hdr[1] < (1ull << 28) && hdr[2] < (1ull << 24) && hdr[3] <= 16;
+        if (ok && !objPath.empty()) {
+            struct stat sb{};
+            ok = ::stat(objPath.c_str(), &sb) == 0 && hdr[4] == static_cast<uint64_t>(sb.st_size) &&
+                 hdr[5] == static_cast<uint64_t>(sb.st_mtim.tv_sec) && hdr[6] == static_cast<uint64_t>(sb.st_mtim.tv_nsec);
+        }
+        std::vector<Triangle> tris;
+        std::vector<int> order;
+        std::vector<std::shared_ptr<Material>> mats;
+        std::vector<Light> ls;
+        if (ok) {
+            tris.resize(hdr[1]); order.resize(hdr[1]);
+            if (hdr[1]) ok = std::fread(tris.data(), sizeof(Triangle), tris.size(), f) == tris.size() && std::fread(order.data(), sizeof(int), order.size(), f) == order.size();
+            for (uint64_t i = 0; ok && i < hdr[2]; ++i) {
+                float rec[8];
+                ok = std::fread(rec, sizeof(rec), 1, f) == 1;
+                auto m = std::make_shared<Material>();
+                m->type = static_cast<MaterialType>(static_cast<int>(rec[0])); m->albedo = vec3(rec[1], rec[2], rec[3]);
+                m->roughness = rec[4]; m->metallic = rec[5]; m->ior = rec[6];
+                mats.push_back(m);
+            }
+            for (uint64_t i = 0; ok && i < hdr[3]; ++i) {
+                float rec[7];
+                ok = std::fread(rec, sizeof(rec), 1, f) == 1;
+                ls.emplace_back(vec3(rec[0], rec[1], rec[2]), vec3(rec[3], rec[4], rec[5]), rec[6]);
+            }
+            ok = ok && std::fgetc(f) == EOF;
+        }
+        std::fclose(f);
+        if (!ok) return false;
+        triangles.swap(tris); buildOrder.swap(order); materials.swap(mats); lights.swap(ls);
+        return true;
+    }
+
+    // loadFromObj through the cache `cachePath` (default: <obj>.b2ptscene next to the OBJ).  Same result either way.
+    bool loadFromObjCached(const std::string& objPath, std::string cachePath = std::string()) {
+        if (cachePath.empty()) cachePath = objPath + ".b2ptscene";
+        const std::vector<Light> keep = lights;
+        if (loadCache(cachePath, objPath)) { lights = keep; return true; }
+        if (!loadFromObj(objPath)) return false;
+        saveCache(cachePath, objPath);   // best effort: a read-only directory just means no cache
+        return true;
     }
 
     bool loadFromObj(const std::string& objPath) {

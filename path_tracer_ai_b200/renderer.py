@@ -33,6 +33,7 @@ def _host_lib():
     if not getattr(L, "_host_ready", False):
         vp = C.c_void_p
         L.b2pt_scene_load_obj.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.b2pt_scene_load_obj_cached.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
         L.b2pt_scene_free.argtypes = [vp]
         L.b2pt_scene_free.restype = None
         L.b2pt_scene_num_triangles.argtypes = [vp]
@@ -51,7 +52,7 @@ def _host_lib():
     return L
 
 
-HOST_EXPORTS = ["b2pt_scene_load_obj", "b2pt_scene_free", "b2pt_scene_num_triangles", "b2pt_scene_num_materials",
+HOST_EXPORTS = ["b2pt_scene_load_obj", "b2pt_scene_load_obj_cached", "b2pt_scene_free", "b2pt_scene_num_triangles", "b2pt_scene_num_materials",
                 "b2pt_scene_num_lights", "b2pt_scene_get_triangles", "b2pt_scene_get_materials", "b2pt_scene_get_lights",
                 "b2pt_camera_look_at", "b2pt_write_png", "b2pt_write_pfm", "b2pt_obj_parser_selfcheck"]
 
@@ -86,10 +87,15 @@ class Scene:
         self.materials8 = np.zeros((0, 8), np.float32)
         self.lights = list(_capi.REFERENCE_LIGHTS)
 
-    def loadFromObj(self, path: str) -> bool:
+    def loadFromObj(self, path: str, cache: bool | str = False) -> bool:
+        """cache: True / a file name = go through the binary scene cache (b2pt_scene_load_obj_cached)."""
         L = _host_lib()
         h = C.c_void_p()
-        if L.b2pt_scene_load_obj(os.fsencode(path), C.byref(h)) != 0:
+        if cache:
+            rc = L.b2pt_scene_load_obj_cached(os.fsencode(path), None if cache is True else os.fsencode(cache), C.byref(h))
+        else:
+            rc = L.b2pt_scene_load_obj(os.fsencode(path), C.byref(h))
+        if rc != 0:
             return False
         try:
             n = L.b2pt_scene_num_triangles(h)

@@ -11,6 +11,20 @@ Outputs (small, committed):
   render_cornell.npz  reference Renderer::render of the Cornell scene, 32x18, 262144 spp, 5 bounces
                       (float framebuffer) + the scene arrays (pre-build order) so that tests do not
                       depend on OBJ parsing.
+  render_mesh.npz     reference Renderer::render of a 6,000-triangle tessellated mesh scene (displaced terrain, tori,
+                      spheres: diffuse, MIRROR, rough specular, GLASS, smooth normals), 32x18, 6 bounces, as four independent
+                      runs of 65536 spp (their mean = a 262144-spp frame; their scatter = the reference's own noise).
+                      The scene generator's roughness-0.1 object is set to 0.35: the reference's SPECULAR direct term is
+                      albedo * D_GGX with no normalisation (renderer.hpp:286-290), peak 1/(pi r^4) = 3183 at r = 0.1, and
+                      two 16384-spp runs of the REFERENCE ITSELF then differ by 57-81 % relRMSE per channel and 2.2 % in mean
+                      luminance (3.7-4.2 % and 0.05 % at r = 0.35) — no finite-sample gate can be stated on it.
+
+  render_c1.npz       BASELINE.md §4's image-parity run: the reference renderer on BASELINE configs[0] — the loader's Cornell
+                      scene at 800x450, 5 bounces — at 4096 spp (1.47 G samples, the better part of an hour on 8 cores),
+                      stored as 10x10-pixel block means (80x45x3 floats): at 4096 spp a single pixel of the reference is
+                      still ~5 % noisy, a block mean is not.
+
+    python tests/golden/make_golden.py [trace|cornell|mesh|c1 ...]     (default: trace cornell mesh)
 """
 import os
 import sys
@@ -35,8 +49,48 @@ def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
+def render_mesh_golden():
+    ms = scenes.mesh_scene(6000, seed=11)
+    m8 = ms["materials8"].copy()
+    m8[5, 4] = 0.35
+    R = RefOracle(ms["pos"], ms["nrm"], ms["mat"], m8)
+    # four INDEPENDENT runs of 65536 spp (the reference seeds itself from std::random_device): their mean is the
+    # 262144-spp golden, their scatter says how far the reference is from ITSELF pixel by pixel
+    W, H, SPP, B, RUNS = 32, 18, 65536, 6, 4
+    runs, secs = [], 0.0
+    for _ in range(RUNS):
+        fb, s1 = R.render(W, H, SPP, B)
+        runs.append(fb); secs += s1
+    runs = np.stack(runs)
+    np.savez_compressed(os.path.join(HERE, "render_mesh.npz"), pos=ms["pos"], nrm=ms["nrm"], mat=ms["mat"], order=R.order(),
+                        materials8=m8, fb_ref=runs.mean(0), fb_runs=runs, spp=SPP * RUNS, bounces=B)
+    print(f"render_mesh: {RUNS} x {W}x{H}x{SPP} in {secs:.1f}s mean {runs.mean():.5f}")
+
+
+def render_c1_golden():
+    tmp = tempfile.mkdtemp()
+    obj = scenes.write_cornell_obj(tmp)
+    sc = pt.Scene()
+    assert sc.loadFromObj(obj)
+    R = RefOracle(obj_path=obj)
+    pre_pos, pre_nrm, pre_mat = prebuild_from_scene(sc)
+    W, H, SPP, B, K = 800, 450, 4096, 5, 10
+    fb, secs = R.render(W, H, SPP, B)
+    blocks = fb.reshape(H // K, K, W // K, K, 3).mean((1, 3)).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "render_c1.npz"), pos=pre_pos, nrm=pre_nrm, mat=pre_mat, order=sc.order,
+                        materials8=sc.materials8, blocks_ref=blocks, block=K, width=W, height=H, spp=SPP, bounces=B)
+    print(f"render_c1: {W}x{H}x{SPP} in {secs:.1f}s mean {fb.mean():.5f}")
+
+
 def main():
     oracle.build("ref")
+    what = set(sys.argv[1:]) or {"trace", "cornell", "mesh"}
+    if "mesh" in what:
+        render_mesh_golden()
+    if "c1" in what:
+        render_c1_golden()
+    if not ({"trace", "cornell"} & what):
+        return
     rng = np.random.default_rng(20261018)
 
     pos = scenes.random_soup(2000, 42)

@@ -6,8 +6,9 @@ import os
 import numpy as np
 import pytest
 
+import oracle
 import path_tracer_ai_b200 as pt
-from oracle import PortOracle
+from oracle import PortOracle, RefOracle
 from path_tracer_ai_b200 import scenes
 
 from conftest import bits
@@ -23,13 +24,28 @@ def rays(n, seed, extent=1.2, centre=(0, 0, 0)):
     return o, d
 
 
-def check_closest(eng, P, o, d, tmax=None):
+def check_closest(eng, P, o, d, tmax=None, ref=None):
+    """GPU (through the C ABI) vs the CPU restatement, and — when `ref` is given — vs THE REFERENCE ITSELF
+    (oracle/_ref: the unmodified headers; its BVH is built from the same pre-build triangle list): ids and t bits."""
     tri, t, uv = eng.trace_closest(o, d, tmax)
     rt, rtt, ruv = P.trace_closest(o, d, tmax)
     assert np.array_equal(tri, rt), f"{int((tri != rt).sum())} of {len(tri)} ids differ"
     assert np.array_equal(bits(t), bits(rtt))
     assert np.array_equal(bits(uv), bits(ruv))
+    if ref is not None:
+        ft, ftt = ref.trace_closest(o, d, tmax)
+        assert np.array_equal(tri, ft), f"{int((tri != ft).sum())} of {len(tri)} ids differ from the reference's own intersector"
+        assert np.array_equal(bits(t), bits(ftt))
     return tri
+
+
+def reference_of(pos_prebuild, P):
+    """The reference's own BVH over the same triangles (None if oracle/_ref was not built); its order must be ours."""
+    if not oracle.ref_available() or len(pos_prebuild) == 0:
+        return None
+    R = RefOracle(pos_prebuild)
+    assert np.array_equal(R.order(), P.order())
+    return R
 
 
 def upload(eng, P):
@@ -44,7 +60,7 @@ def test_small_and_ragged_triangle_counts(engine, ntri):
     assert np.array_equal(pt.reference_order(pos), P.order())
     upload(engine, P)
     o, d = rays(30011, ntri)   # ragged: not a multiple of the block size
-    check_closest(engine, P, o, d)
+    check_closest(engine, P, o, d, ref=reference_of(pos, P))
     occ = engine.trace_any(o, d)
     assert np.array_equal(occ, P.trace_any(o, d))
 
@@ -83,7 +99,7 @@ def test_mesh_scene_with_vertex_aimed_rays(engine):
     rng = np.random.default_rng(6)
     half = len(o) // 2
     d[:half] = V[rng.integers(0, len(V), half)] - o[:half]
-    check_closest(engine, P, o, d)
+    check_closest(engine, P, o, d, ref=reference_of(ms["pos"], P))
 
 
 def test_axis_aligned_geometry_reference_quirks(engine):
@@ -100,16 +116,68 @@ def test_axis_aligned_geometry_reference_quirks(engine):
     P = PortOracle(pos)
     upload(engine, P)
     o, d = rays(400000, 12, extent=1.5)
-    check_closest(engine, P, o, d)
+    R = reference_of(pos, P)
+    check_closest(engine, P, o, d, ref=R)
     # rays straight down / along axes (zero direction components -> inf / NaN slabs)
     o2 = o.copy()
     d2 = np.zeros_like(d)
     d2[:, 1] = -1.0
     d2[::3] = [1.0, 0.0, 0.0]
     d2[1::3] = [0.0, 0.0, -1.0]
-    check_closest(engine, P, o2, d2)
+    check_closest(engine, P, o2, d2, ref=R)
     assert np.array_equal(engine.trace_any(o2, d2), P.trace_any(o2, d2))
     assert engine.stats()["shadow_rays"] == len(o2)
+
+
+def big_triangles(n, seed, extent, size):
+    rng = np.random.default_rng(seed)
+    c = (rng.random((n, 1, 3)) * 2 - 1) * extent
+    return (c + (rng.random((n, 3, 3)) - 0.5) * size).reshape(n, 9).astype(np.float32)
+
+
+@pytest.mark.parametrize("flags", [0, pt.FLAG_LANE_KERNELS, pt.FLAG_POOL_EXTEND])
+def test_hoisted_leaves_and_scenes_that_are_all_hoisted(built, flags):
+    """Leaves whose box covers most of the scene are kept out of the traversal tree and tested up front (ctx.cuh):
+    a soup inside a few room-sized triangles (the loader's situation), and a scene of nothing but huge triangles
+    (every leaf hoisted, no tree at all)."""
+    eng = pt.Engine(flags=flags)
+    for pos in (np.concatenate([big_triangles(8, 1, 0.3, 6.0), scenes.random_soup(6000, 2)]),
+                big_triangles(10, 3, 0.2, 5.0),
+                big_triangles(40, 4, 0.5, 4.0)):
+        P = PortOracle(pos)
+        upload(eng, P)
+        info = eng.accel_info()
+        assert info["hoisted_leaves"] >= 1, info
+        o, d = rays(200000, 17, extent=2.0)
+        check_closest(eng, P, o, d, ref=reference_of(pos, P))
+        tm = np.random.default_rng(5).random(len(o)).astype(np.float32) * 3
+        assert np.array_equal(eng.trace_any(o, d, tm), P.trace_any(o, d, tm))
+    eng.close()
+
+
+def test_large_coordinates_large_triangles_near_surface_grazing_rays(engine):
+    """The distance cull of the ordered traversal skips subtrees entered later than best*(1+2^-10) + 2^-12*(R+|o|)
+    (traverse.cuh): Möller–Trumbore's t has an ABSOLUTE error that grows with the triangle's size and distance, so a
+    purely relative slack is not safe for big triangles far from the origin hit from close by at grazing angles."""
+    rng = np.random.default_rng(77)
+    centre = np.float32([900.0, -400.0, 650.0])
+    pos = big_triangles(4000, 5, 40.0, 25.0) + np.tile(centre, 3)
+    P = PortOracle(pos)
+    upload(engine, P)
+    V = P.triangles()[0].reshape(-1, 3, 3)
+    n = 300000
+    k = rng.integers(0, len(V), n)
+    w = rng.random((n, 3)).astype(np.float32); w /= w.sum(1, keepdims=True)
+    on = (V[k] * w[:, :, None]).sum(1)                                   # a point on triangle k
+    nrm = np.cross(V[k, 1] - V[k, 0], V[k, 2] - V[k, 0]); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True) + 1e-30
+    tang = V[k, 1] - V[k, 0]; tang /= np.linalg.norm(tang, axis=1, keepdims=True) + 1e-30
+    lift = (10.0 ** rng.uniform(-3.0, -0.5, (n, 1))).astype(np.float32)   # 0.001 .. 0.3 above the surface
+    o = (on + nrm * lift).astype(np.float32)
+    graze = (10.0 ** rng.uniform(-4.0, 0.0, (n, 1))).astype(np.float32)
+    d = (tang - nrm * graze).astype(np.float32)                          # towards the surface at 0.006 .. 45 degrees
+    check_closest(engine, P, o, d, ref=reference_of(pos, P))
+    o2, d2 = rays(200000, 3, extent=60.0, centre=centre)
+    check_closest(engine, P, o2, d2)
 
 
 @pytest.mark.parametrize("flags", [0, pt.FLAG_LANE_KERNELS, pt.FLAG_POOL_EXTEND, pt.FLAG_EXACT_ONLY])

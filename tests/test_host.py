@@ -136,6 +136,29 @@ def test_chunked_obj_parser_equals_line_by_line(built, tmp_path):
     assert L.b2pt_obj_parser_selfcheck(os.fsencode(str(tmp_path / "empty.obj")), 4, 1) == 0
 
 
+def test_binary_scene_cache_roundtrip(built, tmp_path):
+    """The scene cache returns exactly what the loader builds (triangles in post-build order, order, materials),
+    is rejected once the OBJ changes, and a corrupt cache falls back to parsing."""
+    obj = scenes.write_cornell_obj(str(tmp_path))
+    a = pt.Scene(); assert a.loadFromObj(obj)
+    b = pt.Scene(); assert b.loadFromObj(obj, cache=True)              # writes <obj>.b2ptscene
+    assert os.path.exists(obj + ".b2ptscene")
+    c = pt.Scene(); assert c.loadFromObj(obj, cache=True)              # reads it
+    for x in (b, c):
+        assert np.array_equal(bits(x.pos), bits(a.pos)) and np.array_equal(bits(x.nrm), bits(a.nrm))
+        assert np.array_equal(x.mat, a.mat) and np.array_equal(x.order, a.order) and np.array_equal(x.materials8, a.materials8)
+        assert x.lights == a.lights
+    # a changed OBJ invalidates the cache
+    text = open(obj).read()
+    open(obj, "w").write(text + "v 9 9 9\nv 9.1 9 9\nv 9 9.1 9\nusemtl diffuse_white\nf -3 -2 -1\n")
+    d = pt.Scene(); assert d.loadFromObj(obj, cache=True)
+    assert len(d.pos) == len(a.pos) + 1
+    # garbage in the cache file: ignored
+    open(obj + ".b2ptscene", "wb").write(b"not a cache")
+    e = pt.Scene(); assert e.loadFromObj(obj, cache=True)
+    assert np.array_equal(bits(e.pos), bits(d.pos))
+
+
 def test_obj_out_of_range_normal_and_texcoord_indices(built, tmp_path):
     """An OBJ whose faces name normals / texture coordinates that do not exist must not crash the loader: those
     references are treated as absent (the loader then uses the face normal), a missing VERTEX fails the load."""
