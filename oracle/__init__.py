@@ -211,6 +211,9 @@ class RefOracle:
             L.ref_render.restype = C.c_double
             L.ref_render.argtypes = [C.c_void_p, f32p, f32p, f32p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int]
+            L.ref_render_window.restype = C.c_double
+            L.ref_render_window.argtypes = [C.c_void_p, f32p, f32p, f32p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
             L.ref_camera_ray.argtypes = [f32p, f32p, f32p, C.c_float, f32p, C.c_int64, f32p]
             L.ref_camera_basis.argtypes = [f32p, f32p, f32p, C.c_float, f32p]
             L.ref_tree_stats.argtypes = [C.c_void_p, i64p]
@@ -279,6 +282,16 @@ class RefOracle:
         fb = np.zeros((height, width, 3), np.float32)
         secs = self.lib().ref_render(self.h, _f32(cam["pos"]), _f32(cam["target"]), _f32(cam["up"]), cam["fov"],
                                      width, height, spp, bounces, _ptr(fb), nthreads)
+        return fb, secs
+
+    def render_window(self, width, height, window, spp, bounces, cam=DEFAULT_CAM, nthreads=0):
+        """The reference's per-sample code (camera ray + tracePath) on the pixels of window = (x0, y0, x1, y1) of a
+        width x height frame, `spp` samples per pixel split over independent Renderer objects — one per thread, so the
+        member RNG that Renderer::render races under OpenMP is private to each.  Returns (fb[y1-y0, x1-x0, 3], seconds)."""
+        x0, y0, x1, y1 = window
+        fb = np.zeros((y1 - y0, x1 - x0, 3), np.float32)
+        secs = self.lib().ref_render_window(self.h, _f32(cam["pos"]), _f32(cam["target"]), _f32(cam["up"]), cam["fov"],
+                                            width, height, x0, y0, x1, y1, spp, bounces, _ptr(fb), nthreads)
         return fb, secs
 
     @classmethod

@@ -255,7 +255,41 @@ bool Scene::loadFromObj(const std::string& objPath) {
 // Renderer::saveImage — declared at reference include/renderer.hpp:104.  The harness variant
 // copies the float framebuffer to the address encoded as "mem:<hex>" (W*H*3 floats).
 // ---------------------------------------------------------------------------------------------
+// Request block of the "win:" variant (ref_render_window below).
+struct WindowJob {
+    const Scene* scene; const Camera* camera;
+    int x0, y0, x1, y1;      // pixel window [x0,x1) x [y0,y1)
+    int spp;                 // samples per pixel taken by THIS Renderer
+    unsigned jitter_seed;
+    double* sum;             // (y1-y0)*(x1-x0)*3 running sums of the valid samples
+    long long* valid;        // (y1-y0)*(x1-x0) number of valid samples
+};
+
 void Renderer::saveImage(const std::string& filename) {
+    if (filename.compare(0, 4, "win:") == 0) {
+        // The per-sample body of Renderer::render (renderer.hpp:62-72) for the pixels of a window, run SERIALLY on this
+        // Renderer: jitter from a local mt19937 as in :55-56, tracePath with this object's own `rng`.  No thread shares
+        // the generator, so unlike render() under OpenMP the member RNG is not raced.
+        auto* job = reinterpret_cast<WindowJob*>(static_cast<uintptr_t>(std::strtoull(filename.c_str() + 4, nullptr, 16)));
+        std::mt19937 localRng(job->jitter_seed);
+        std::uniform_real_distribution<float> localDist(0.0f, 1.0f);
+        const int ww = job->x1 - job->x0;
+        for (int y = job->y0; y < job->y1; ++y)
+            for (int x = job->x0; x < job->x1; ++x) {
+                const size_t k = static_cast<size_t>(y - job->y0) * ww + (x - job->x0);
+                for (int s = 0; s < job->spp; ++s) {
+                    float u = (x + localDist(localRng)) / (settings.width - 1);
+                    float v = (y + localDist(localRng)) / (settings.height - 1);
+                    Ray ray = job->camera->getRay(u, v);
+                    glm::vec3 sample = tracePath(ray, *job->scene, 0);
+                    if (isValidColor(sample, "Sample computation")) {
+                        job->sum[3 * k + 0] += sample.x; job->sum[3 * k + 1] += sample.y; job->sum[3 * k + 2] += sample.z;
+                        job->valid[k] += 1;
+                    }
+                }
+            }
+        return;
+    }
     if (filename.compare(0, 4, "mem:") != 0) return;
     float* dst = reinterpret_cast<float*>(static_cast<uintptr_t>(std::strtoull(filename.c_str() + 4, nullptr, 16)));
     for (size_t i = 0; i < frameBuffer.size(); ++i) {
@@ -437,6 +471,44 @@ double ref_render(void* h, const float* cam_pos, const float* cam_target, const 
         char name[64];
         std::snprintf(name, sizeof(name), "mem:%llx", static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(fb)));
         renderer.saveImage(name);
+    }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// The reference's per-sample code (camera ray + tracePath) for a pixel window, `spp` samples per pixel split over
+// `nthreads` INDEPENDENT Renderer objects (one per thread, each with its own member RNG): the race-free reading of
+// renderer.hpp:53-81.  fb: (y1-y0)*(x1-x0)*3 floats = sum of valid samples / spp.  Returns seconds.
+double ref_render_window(void* h, const float* cam_pos, const float* cam_target, const float* cam_up, float fov,
+                         int width, int height, int x0, int y0, int x1, int y1, long long spp, int bounces, float* fb,
+                         int nthreads) {
+    CoutMute mute;
+    auto rs = static_cast<RefScene*>(h);
+    Camera camera(glm::vec3(cam_pos[0], cam_pos[1], cam_pos[2]), glm::vec3(cam_target[0], cam_target[1], cam_target[2]),
+                  glm::vec3(cam_up[0], cam_up[1], cam_up[2]), fov);
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    const size_t npx = static_cast<size_t>(y1 - y0) * (x1 - x0);
+    std::vector<std::vector<double>> sums(nthreads, std::vector<double>(npx * 3, 0.0));
+    std::vector<std::vector<long long>> valid(nthreads, std::vector<long long>(npx, 0));
+    std::random_device rd;
+    std::vector<unsigned> seeds(nthreads);
+    for (auto& s : seeds) s = rd();
+    auto t0 = std::chrono::high_resolution_clock::now();
+    #pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+    for (int t = 0; t < nthreads; ++t) {
+        Renderer::Settings settings;
+        settings.width = width; settings.height = height; settings.maxBounces = bounces;
+        settings.samplesPerPixel = static_cast<int>(spp / nthreads + (t < spp % nthreads ? 1 : 0));
+        Renderer renderer(settings);
+        WindowJob job{rs->scene.get(), &camera, x0, y0, x1, y1, settings.samplesPerPixel, seeds[t], sums[t].data(), valid[t].data()};
+        char name[64];
+        std::snprintf(name, sizeof(name), "win:%llx", static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(&job)));
+        renderer.saveImage(name);
+    }
+    auto t1 = std::chrono::high_resolution_clock::now();
+    for (size_t k = 0; k < npx * 3; ++k) {
+        double s = 0.0;
+        for (int t = 0; t < nthreads; ++t) s += sums[t][k];
+        fb[k] = static_cast<float>(s / static_cast<double>(spp));
     }
     return std::chrono::duration<double>(t1 - t0).count();
 }

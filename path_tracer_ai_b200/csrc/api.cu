@@ -112,6 +112,10 @@ int b2pt_create(const b2pt_config* cfg, b2pt_ctx** out) {
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev2)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev3)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaHostAlloc((void**)&ctx->h_count, 64, cudaHostAllocDefault)) != cudaSuccess) return fail(e, "cudaHostAlloc");
     if ((e = cudaMalloc(&ctx->d_counters, sizeof(TraceCounters))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_fallback_count, 64)) != cudaSuccess) return fail(e, "cudaMalloc");
     *out = ctx;
@@ -122,6 +126,7 @@ void b2pt_destroy(b2pt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->side) cudaStreamSynchronize(ctx->side);
     free_scene(ctx);
     for (int i = 0; i < B2PT_SCRATCH_SLOTS; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -131,6 +136,10 @@ void b2pt_destroy(b2pt_ctx* ctx) {
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

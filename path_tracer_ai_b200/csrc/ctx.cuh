@@ -83,6 +83,11 @@ struct b2pt_ctx {
     int64_t max_paths = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    // render_frame: the exact recursion of the uncertified rays runs on `side` while the main stream sorts the bounce
+    // (fork / join through ev_fork / ev_join); h_count = pinned word the per-bounce active count is read back into
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int* h_count = nullptr;
     std::vector<cudaEvent_t> ev_pool;    // per-bounce timing events of render_frame, created once and reused
     bool debug_sync = false;             // B2PT_DEBUG_SYNC=1 at b2pt_create: synchronise after every render kernel
     std::string err;

@@ -25,6 +25,8 @@
 #include <cstring>
 #include <cstdlib>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "traverse_pool.cuh"
 #include "traverse_rtc.cuh"
 
@@ -160,6 +162,32 @@ __device__ __forceinline__ void block_append(int* counter, int* queue, bool pred
     }
     __syncthreads();
     if (pred) queue[s_base + s_w[w] + __popc(b & ((1u << lane) - 1u))] = value;
+}
+
+// The same append with the block's entries grouped by `bin` (0..7, -1 = nothing to append): k_shade groups the next
+// rays of its 256 neighbouring vertices by direction octant, so a warp of the next closest-hit launch holds rays that
+// start close together AND head the same way.
+__device__ __forceinline__ void block_append_binned(int* counter, int* queue, int bin, int value) {
+    __shared__ int s_cnt[8 * B2PT_BIN_WARPS];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x < 8 * B2PT_BIN_WARPS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned m = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && lane == __ffs(m) - 1) s_cnt[bin * B2PT_BIN_WARPS + w] = __popc(m);
+    __syncthreads();
+    if (w == 0) {   // exclusive scan of the 64 (bin, warp) counts: two per lane + a warp scan
+        static_assert(8 * B2PT_BIN_WARPS == 64, "two entries per lane");
+        const int v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1];
+        int incl = v0 + v1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+        const int excl = incl - v0 - v1;
+        s_cnt[2 * lane] = excl; s_cnt[2 * lane + 1] = excl + v0;
+        if (lane == 31) s_base = incl ? atomicAdd(counter, incl) : 0;
+    }
+    __syncthreads();
+    if (bin >= 0) queue[s_base + s_cnt[bin * B2PT_BIN_WARPS + w] + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
 // The one-pass counting sort after a closest hit: the path goes into the queue of its material type, and one
@@ -384,6 +412,50 @@ __global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) 
     }
 }
 
+// ---- hit-point order --------------------------------------------------------------------------------------------------
+// From the first bounce on the paths of a batch hit the scene all over the place, and queue neighbours (neighbouring
+// pixels) stop being spatial neighbours: the shadow rays and the next bounce rays of a warp then start in 32 unrelated
+// corners of the tree.  Before k_hitinfo bins a bounce, its paths are therefore put in the Morton order of their hit
+// points (one radix sort of (key, path slot) pairs per bounce; the camera rays' hits too — a 3D-compact block of
+// vertices beats a scanline run of pixels: depth-0 shadow launch 18.6 -> ms at 32M paths): a block of k_hitinfo then holds 256 neighbouring
+// vertices, its light-major shadow entries are 32 near-identical rays per warp, and k_shade appends the next rays in
+// the same order, so the next closest-hit launch reads origin-sorted rays.  The key is only an ORDER (computed with an
+// FMA, quantised to 1024^3 cells of the scene's coordinate range): no result depends on it — every path's arithmetic
+// is a function of its own state and k_resolve adds samples in sample order.
+#ifndef B2PT_SORT_BEGIN_BIT
+#define B2PT_SORT_BEGIN_BIT 6     // the 24 high bits of the 30-bit Morton code: three 8-bit radix passes, 256^3 cells
+#endif
+__device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+// keys[k] / vals[k] for k < P: entry k of the active queue (slot, Morton key of its hit point); misses and the tail
+// beyond the queue get the largest key.  The sort is stable, so the first *count_ptr sorted entries are the queue's.
+__global__ void __launch_bounds__(256) k_sort_keys(Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr, int P,
+                                                    float bound, uint32_t* __restrict__ keys, int* __restrict__ vals) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    const int total = list ? *count_ptr : P;
+    uint32_t key = 0x3FFFFFFFu;
+    int p = -1;
+    if (k < total) {
+        p = list ? list[k] : k;
+        float4 h = W.hit[p];
+        if (__float_as_int(h.y) >= 0) {
+            float4 o = W.ro[p], d = W.rd[p];
+            const float sc = 512.0f / bound;
+            float x = fmaf(fmaf(d.x, h.x, o.x), sc, 512.0f), y = fmaf(fmaf(d.y, h.x, o.y), sc, 512.0f), z = fmaf(fmaf(d.z, h.x, o.z), sc, 512.0f);
+            uint32_t xi = (uint32_t)fminf(fmaxf(x, 0.0f), 1023.0f), yi = (uint32_t)fminf(fmaxf(y, 0.0f), 1023.0f), zi = (uint32_t)fminf(fmaxf(z, 0.0f), 1023.0f);
+            key = morton_spread10(xi) | (morton_spread10(yi) << 1) | (morton_spread10(zi) << 2);
+        }
+    }
+    keys[k] = key; vals[k] = p;
+}
+
 // Hit record -> hit point / shading normal / material, and the one-pass counting sort by material type.
 __global__ void __launch_bounds__(B2PT_BIN_BLOCK) k_hitinfo(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr, int P) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,12 +517,13 @@ __device__ __forceinline__ V3 direct_lighting(const DeviceScene& S, const DMater
     return total;
 }
 
-// tracePath's material switch (renderer.hpp:166-247) for one vertex of material type TYPE; returns whether the
-// path continues (its next ray is then in ro/rd).
+// tracePath's material switch (renderer.hpp:166-247) for one vertex of material type TYPE; returns -1 when the path
+// ends, else the direction octant (sign bits) of its next ray, which is then in ro/rd.
+__device__ __forceinline__ int octant_of(V3 d) { return (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0); }
 template <int TYPE>
-__device__ __forceinline__ bool shade_vertex(const DeviceScene& S, const Wave& W, const FrameConst& F, long long pix_begin, int npc, int s_begin,
+__device__ __forceinline__ int shade_vertex(const DeviceScene& S, const Wave& W, const FrameConst& F, long long pix_begin, int npc, int s_begin,
                                              int depth, int p) {
-    bool cont = false;
+    int cont = -1;
     {
         float4 g0 = W.g0[p], g1 = W.g1[p], d4 = W.rd[p];
         V3 P = f4v(g0), n = f4v(g1), d = f4v(d4);
@@ -482,7 +555,7 @@ __device__ __forceinline__ bool shade_vertex(const DeviceScene& S, const Wave& W
                     V3 nd = vnormalize(dir);   // Ray ctor
                     W.ro[p] = make_float4(no.x, no.y, no.z, 0.0f);
                     W.rd[p] = make_float4(nd.x, nd.y, nd.z, 0.0f);
-                    cont = true;
+                    cont = octant_of(nd);
                 }
             }
         } else {
@@ -518,7 +591,7 @@ __device__ __forceinline__ bool shade_vertex(const DeviceScene& S, const Wave& W
                         W.thr[p] = make_float4(T.x, T.y, T.z, 0.0f);
                         W.ro[p] = make_float4(no.x, no.y, no.z, 0.0f);
                         W.rd[p] = make_float4(nd.x, nd.y, nd.z, 0.0f);
-                        cont = true;
+                        cont = octant_of(nd);
                     }
                 }
             }
@@ -534,7 +607,7 @@ __global__ void __launch_bounds__(B2PT_BIN_BLOCK) k_shade(DeviceScene S, Wave W,
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int c0 = W.counters[C_MAT0], c1 = W.counters[C_MAT1], c2 = W.counters[C_MAT2];
     if (blockIdx.x * blockDim.x >= c0 + c1 + c2) return;   // whole block beyond the queues (uniform)
-    bool cont = false;
+    int cont = -1;
     int p = 0;
     if (k < c0) {
         p = W.q_mat[0][k];
@@ -546,13 +619,14 @@ __global__ void __launch_bounds__(B2PT_BIN_BLOCK) k_shade(DeviceScene S, Wave W,
         p = W.q_mat[2][k - c0 - c1];
         cont = shade_vertex<B2PT_DIELECTRIC>(S, W, F, pix_begin, npc, s_begin, depth, p);
     }
-    block_append(&W.counters[next_slot], W.q_active[next_slot], cont, p);
+    block_append_binned(&W.counters[next_slot], W.q_active[next_slot], cont, p);
 }
 
 // Bookkeeping between bounces (single thread): totals, reset the per-bounce counters.
 __global__ void k_begin_bounce(Wave W, int cur_slot, int first, int P, int nlight) {
     // called BEFORE extend of a depth: the active count of this depth is known here
     int active = first ? P : W.counters[cur_slot];
+    if (first) W.counters[cur_slot] = P;   // depth 0 has no queue; kernels handed a sorted list read the count from here
     W.totals[0] += (unsigned long long)active;
     W.counters[cur_slot ^ 1] = 0;
     W.counters[C_MAT0] = 0; W.counters[C_MAT1] = 0; W.counters[C_MAT2] = 0;
@@ -718,6 +792,20 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     const bool count = (ctx->flags & B2PT_FLAG_COUNT_FETCHES) != 0;
     // closest-hit kernel with the per-vertex epilogue fused in: small trees only (see k_extend_rtc)
     const bool fused = S.nwide <= 64;
+    // hit-point order of the bounces (k_sort_keys): scenes whose rays diverge, i.e. the ones that do not fuse
+    const bool sort_hits = !fused && !(ctx->flags & B2PT_FLAG_NO_SORT);
+    uint32_t *sort_keys[2] = {nullptr, nullptr};
+    int* sort_vals[2] = {nullptr, nullptr};
+    void* sort_temp = nullptr;
+    size_t sort_temp_bytes = 0;
+    if (sort_hits) {
+        void* sb_ = nullptr;
+        if ((rc = scratch_reserve(ctx, 13, 4 * qi, &sb_))) return rc;
+        sort_keys[0] = (uint32_t*)sb_; sort_keys[1] = sort_keys[0] + Pmax; sort_vals[0] = (int*)(sort_keys[1] + Pmax); sort_vals[1] = sort_vals[0] + Pmax;
+        B2PT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, sort_temp_bytes, sort_keys[0], sort_keys[1], sort_vals[0], sort_vals[1], (int)Pmax,
+                                                       B2PT_SORT_BEGIN_BIT, 30, stream));
+        if ((rc = scratch_reserve(ctx, 14, sort_temp_bytes + 16, &sort_temp))) return rc;
+    }
     int64_t launches = 0, n_extend = 0, n_shadow = 0;
     float extend_ms = 0.0f, shadow_ms = 0.0f;
     // Traversal time is measured with events around extend + direct of every bounce; they come from a pool owned by
@@ -753,7 +841,11 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
             int sabs = s_begin + sb;
             k_raygen<<<(P + 255) / 256, 256, 0, stream>>>(Wv, C, F, pix_begin, npc, sabs, P);
             dbg("k_raygen", pix_begin, sb, -1);
-            for (int depth = 0; depth < st->max_bounces; ++depth) {
+            // A = number of paths the kernels of this depth are launched for: the exact active count, read back after every
+            // k_shade, when the bounces are sorted (grids, sort sizes and the end of the loop follow the surviving paths);
+            // otherwise P, with the kernels leaving early beyond the device-side count.
+            int A = P;
+            for (int depth = 0; depth < st->max_bounces && A > 0; ++depth) {
                 int cur = depth & 1;
                 k_begin_bounce<<<1, 1, 0, stream>>>(Wv, cur, depth == 0, P, S.nlight);
                 dbg("k_begin_bounce", pix_begin, sb, depth);
@@ -762,26 +854,46 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 // Shadow rays of the bounces of a scene big enough for a warp's rays to diverge take the phase-split pool
                 // kernel (1M-triangle scene, 32M-path batches: shadow 1276 -> 1167 ms per frame); closest hit stays with the
                 // run-to-completion kernel, which the pool variant does not beat (850 vs 801 ms): B2PT_FLAG_POOL_EXTEND.
-                const bool pooled = !fused && depth > 0 && !(ctx->flags & B2PT_FLAG_LANE_KERNELS);
-                const unsigned pgrid = (unsigned)std::min<long long>(((long long)P + B2PT_PBLOCK * B2PT_PR - 1) / (B2PT_PBLOCK * B2PT_PR), (long long)ctx->sm_count * 8);
+                // With the bounces in hit-point order (sort_hits) the shadow rays of a warp are near-identical again and the
+                // run-to-completion kernel wins (16 spp, 32M paths: sorted + pool 61 ms, sorted + rtc 42 ms, unsorted + pool 73 ms).
+                const bool pooled = !fused && depth > 0 && !sort_hits && !(ctx->flags & B2PT_FLAG_LANE_KERNELS);
+                const unsigned pgrid = (unsigned)std::min<long long>(((long long)A + B2PT_PBLOCK * B2PT_PR - 1) / (B2PT_PBLOCK * B2PT_PR), (long long)ctx->sm_count * 8);
                 if (pooled && (ctx->flags & B2PT_FLAG_POOL_EXTEND)) {
                     if (count) k_extend_pool<true><<<pgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                     else k_extend_pool<false><<<pgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 } else if (fused) {
-                    if (count) k_extend_rtc<true, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    else k_extend_rtc<false, true><<<(P + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    if (count) k_extend_rtc<true, true><<<(A + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else k_extend_rtc<false, true><<<(A + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 } else {
-                    if (count) k_extend_rtc<true, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    else k_extend_rtc<false, false><<<(P + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    if (count) k_extend_rtc<true, false><<<(A + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    else k_extend_rtc<false, false><<<(A + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 }
                 dbg("k_extend", pix_begin, sb, depth);
                 if (fused) {   // k_extend_rtc has already run the epilogue of its certified rays
                     k_extend_fallback<true><<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
                     dbg("k_extend_fallback", pix_begin, sb, depth);
+                } else if (sort_hits) {
+                    // The exact recursion of the handful of uncertified rays (a fraction of a millisecond of pure latency) runs
+                    // on the side stream while this one sorts the bounce; k_sort_keys may read a hit record the recursion is
+                    // about to replace — the key is only an order.
+                    B2PT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, stream));
+                    B2PT_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+                    k_extend_fallback<false><<<ctx->sm_count * 4, 128, 0, ctx->side>>>(S, Wv);
+                    B2PT_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+                    ++launches;
+                    k_sort_keys<<<(A + 255) / 256, 256, 0, stream>>>(Wv, list, &Wv.counters[cur], A, S.coord_bound, sort_keys[0], sort_vals[0]);
+                    dbg("k_sort_keys", pix_begin, sb, depth);
+                    size_t tb = sort_temp_bytes;
+                    B2PT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_temp, tb, sort_keys[0], sort_keys[1], sort_vals[0], sort_vals[1], A,
+                                                                   B2PT_SORT_BEGIN_BIT, 30, stream));
+                    launches += 4;   // histogram + three onesweep passes
+                    B2PT_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_join, 0));
+                    k_hitinfo<<<(A + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, sort_vals[1], &Wv.counters[cur], P);
+                    dbg("k_hitinfo", pix_begin, sb, depth);
                 } else {
                     k_extend_fallback<false><<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
                     dbg("k_extend_fallback", pix_begin, sb, depth);
-                    k_hitinfo<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
+                    k_hitinfo<<<(A + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P);
                     dbg("k_hitinfo", pix_begin, sb, depth);
                 }
                 k_after_extend<<<1, 1, 0, stream>>>(Wv, S.nlight);
@@ -790,8 +902,8 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 ++n_extend;
                 if (S.nlight > 0) {
                     ++n_shadow;
-                    unsigned sg = (unsigned)(((long long)P * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
-                    const unsigned spgrid = (unsigned)std::min<long long>(((long long)P * S.nlight + B2PT_PBLOCK * B2PT_PR - 1) / (B2PT_PBLOCK * B2PT_PR), (long long)ctx->sm_count * 8);
+                    unsigned sg = (unsigned)(((long long)A * S.nlight + B2PT_SHD_BLOCK - 1) / B2PT_SHD_BLOCK);
+                    const unsigned spgrid = (unsigned)std::min<long long>(((long long)A * S.nlight + B2PT_PBLOCK * B2PT_PR - 1) / (B2PT_PBLOCK * B2PT_PR), (long long)ctx->sm_count * 8);
                     if (learn_batch) k_shadow_learn<<<sg, B2PT_SHD_BLOCK, 0, stream>>>(S, Wv, ctx->d_order_stats, ctx->d_order_stats + 8 * (size_t)S.nwide);
                     else if (pooled && count) k_shadow_pool<true><<<spgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
                     else if (pooled) k_shadow_pool<false><<<spgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, ctx->d_counters);
@@ -801,8 +913,13 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 }
                 ev();
                 int nxt = cur ^ 1;
-                k_shade<<<(P + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
+                k_shade<<<(A + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, F, pix_begin, npc, sabs, depth, nxt);
                 dbg("k_shade", pix_begin, sb, depth);
+                if (sort_hits && depth + 1 < st->max_bounces) {
+                    B2PT_CUDA(ctx, cudaMemcpyAsync(ctx->h_count, &Wv.counters[nxt], sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    B2PT_CUDA(ctx, cudaStreamSynchronize(stream));
+                    A = *ctx->h_count;
+                }
             }
             if (learn_batch) ctx->order_state = 1;
             k_resolve<<<(npc + 255) / 256, 256, 0, stream>>>(Wv, (float4*)accum, pix_begin, npc, ns);

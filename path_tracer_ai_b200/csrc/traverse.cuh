@@ -81,6 +81,33 @@ __device__ __forceinline__ bool box_pass(float4 lo, float4 hi, V3 o, V3 invD, fl
     return tmax > tmin;
 }
 
+// Entry distance of a box in the reference's arithmetic: the running tMin after the three axes (aabb.hpp:13-25).
+__device__ __forceinline__ float box_entry(float4 lo, float4 hi, V3 o, V3 invD) {
+    float tmin = B2PT_TMIN, tmax = B2PT_INF;
+    slab_axis(lo.x, hi.x, o.x, invD.x, tmin, tmax);
+    slab_axis(lo.y, hi.y, o.y, invD.y, tmin, tmax);
+    slab_axis(lo.z, hi.z, o.z, invD.z, tmin, tmax);
+    return tmin;
+}
+
+// ---- the certificate ---------------------------------------------------------------------------------------------
+// The fast traversals see a set of CANDIDATES (triangles of visited = visible-at-T0 leaves that Möller–Trumbore accepts
+// in [tMin, T0]); subtrees they skipped were entered later than the final cull distance, so their candidates are
+// farther still.  Let X be the UNIQUE candidate with the smallest t = m, L its reference leaf, e = L's entry distance,
+// and s2 the smallest t among the other candidates seen (+inf if none).  A box that passes at T0 passes at T iff
+// T > e (the running tMax is min(T, far planes) and far > e already).  While the reference recursion runs, ray.tMax is
+// T0 or the t of an accepted candidate — i.e. T0, some value >= s2, or some value beyond the cull distance — until X is
+// accepted.  So if e < min(T0, s2) (and e is not absurdly beyond m, see below) L is entered whenever the recursion
+// reaches it, X is accepted there (m <= ray.tMax), nothing else can be accepted with t <= m afterwards, and the
+// combine picks the smaller t: the reference returns X.  The usual case is e < m; e in [m, s2) is a hit on the entry
+// face of its own leaf box (round 1 sent those to the exact recursion).  e <= m (1 + 2^-12) keeps e well inside the
+// cull slack, so "unseen candidates are beyond e" needs no more than the slack already assumes.  A miss (no candidate)
+// is certified as it is; bit-equal ties at the minimum are not (closest_careful resolves most of them).
+__device__ __forceinline__ bool certify_unique(const DeviceScene& S, const RayQ& r, float m, int leaf, float s2) {
+    const float e = box_entry(__ldg(&S.leaf_lo[leaf]), __ldg(&S.leaf_hi[leaf]), r.o, r.invD);
+    return (e < fminf(s2, r.T0)) & (e <= __fmaf_rn(m, 0.000244140625f, m));
+}
+
 // Does the exact box of reference leaf `leaf` pass the reference slab test with ray.tMax == T?
 __device__ __forceinline__ bool leaf_visible(const DeviceScene& S, int leaf, const RayQ& r, float T) {
     return box_pass(__ldg(&S.leaf_lo[leaf]), __ldg(&S.leaf_hi[leaf]), r.o, r.invD, T);

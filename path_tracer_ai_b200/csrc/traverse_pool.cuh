@@ -49,7 +49,7 @@ namespace b2pt {
 enum { PS_EMPTY = 0, PS_NODE = 1, PS_TRI = 2, PS_DONE = 3 };
 // mutable per-ray state; CUR = wide node to expand (PS_NODE) / next triangle of the current leaf (PS_TRI), TEND = its end
 enum { PF_CUR, PF_TEND, PF_SP, PF_IDX, PF_ANY_COUNT,
-       PF_CULL = PF_ANY_COUNT, PF_BT, PF_BU, PF_BV, PF_BTRI, PF_BLEAF, PF_TIE, PF_CLOSEST_COUNT };
+       PF_CULL = PF_ANY_COUNT, PF_BT, PF_BU, PF_BV, PF_BTRI, PF_BLEAF, PF_TIE, PF_SECOND, PF_CLOSEST_COUNT };
 
 template <bool ANY>
 struct PoolSmem {
@@ -210,7 +210,7 @@ __device__ __forceinline__ void pool_traverse(const DeviceScene& S, PoolSmem<ANY
                         PSET(PF_IDX, r, tag);
                         if constexpr (!ANY) {
                             PSF(PF_CULL, r) = T0; PSF(PF_BT, r) = B2PT_INF; PSF(PF_BU, r) = 0.0f; PSF(PF_BV, r) = 0.0f;
-                            PSET(PF_BTRI, r, -1); PSET(PF_BLEAF, r, -1); PSET(PF_TIE, r, 0);
+                            PSET(PF_BTRI, r, -1); PSET(PF_BLEAF, r, -1); PSET(PF_TIE, r, 0); PSF(PF_SECOND, r) = B2PT_INF;
                         }
                         int sp = 0;
                         if (!ray_has_nan(q)) {   // a NaN ray is a miss in the reference (traverse.cuh): nothing to traverse
@@ -343,8 +343,11 @@ __device__ __forceinline__ void pool_traverse(const DeviceScene& S, PoolSmem<ANY
                         if (tri_fetch_test(S, tri, q, q.T0, t, u, v, leaf)) {
                             if constexpr (ANY) {
                                 occluded = true;
-                            } else if (t <= best) {
+                            } else if (t > best) {
+                                PSF(PF_SECOND, r) = fminf(PSF(PF_SECOND, r), t);
+                            } else {
                                 if (t < best) {
+                                    PSF(PF_SECOND, r) = best;
                                     best = t;
                                     PSF(PF_BT, r) = t; PSF(PF_BU, r) = u; PSF(PF_BV, r) = v; PSET(PF_BTRI, r, tri); PSET(PF_BLEAF, r, leaf);
                                     if (PSI(PF_TIE, r) == 1) PSET(PF_TIE, r, 0);
@@ -378,10 +381,10 @@ __device__ __forceinline__ void pool_traverse(const DeviceScene& S, PoolSmem<ANY
                         HitRec h;
                         h.t = PSF(PF_BT, r); h.tri = PSI(PF_BTRI, r); h.u = PSF(PF_BU, r); h.v = PSF(PF_BV, r);
                         bool certified = PSI(PF_TIE, r) == 0;
-                        if (certified && h.tri >= 0) {   // the winner's reference leaf must still be visible with ray.tMax == t
+                        if (certified && h.tri >= 0) {   // the reference is bound to enter the winner's leaf (traverse.cuh, certify_unique)
                             RayQ q;
-                            q.o = mk3(PC(0, r), PC(1, r), PC(2, r)); q.invD = mk3(PC(6, r), PC(7, r), PC(8, r));
-                            certified = leaf_visible(S, PSI(PF_BLEAF, r), q, h.t);
+                            q.o = mk3(PC(0, r), PC(1, r), PC(2, r)); q.invD = mk3(PC(6, r), PC(7, r), PC(8, r)); q.T0 = PC(9, r);
+                            certified = certify_unique(S, q, h.t, PSI(PF_BLEAF, r), PSF(PF_SECOND, r));
                         }
                         io.store_closest(PSI(PF_IDX, r), h, certified);
                     }

@@ -19,9 +19,9 @@ namespace b2pt {
 // its parent's child box, tested with the reference arithmetic) and that Triangle::intersect accepts in [tMin, T0].
 // Subtrees are skipped when their box fails at T0 (exact, monotone) or when their entry distance exceeds the current
 // best by more than the cull slack (traverse.cuh, cull_after_hit).
-// Returns true when the result is certified to be the reference's answer:
+// Returns true when the result is certified to be the reference's answer (traverse.cuh, certify_unique):
 //   * miss (no candidate), or
-//   * a unique minimum-t candidate whose leaf box still passes the slab test at T = t.
+//   * a unique minimum-t candidate whose leaf the reference recursion is bound to enter.
 template <bool COUNT>
 __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r, HitRec& out,
                                              unsigned& n_nodes, unsigned& n_tris) {
@@ -30,6 +30,7 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
     bool tie = false;
     int best_leaf = -1;
     float best = B2PT_INF;        // t of the current best candidate
+    float second = B2PT_INF;      // smallest t among the other candidates seen (certify_unique)
     float cull = r.T0;            // entry distances above this cannot matter
     // Hoisted leaves (boxes covering most of the scene): tested by every ray, here, while the warp is converged.
     for (int h = 0; h < S.nhoist; ++h) {
@@ -38,12 +39,15 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
         for (int i = first; i < first + cnt; ++i) {
             float t, u, v; int leaf;
             if (COUNT) ++n_tris;
-            if (tri_fetch_test(S, i, r, r.T0, t, u, v, leaf) && t <= best) {
+            if (tri_fetch_test(S, i, r, r.T0, t, u, v, leaf)) {
                 if (t < best) {
+                    second = best;
                     best = t; out.t = t; out.tri = i; out.u = u; out.v = v; tie = false; best_leaf = leaf;
                     cull = cull_after_hit(S, r, t);
-                } else {
+                } else if (t == best) {
                     tie = true;
+                } else {
+                    second = fminf(second, t);
                 }
             }
         }
@@ -80,12 +84,15 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
             for (int i = first; i < first + cnt; ++i) {
                 float t, u, v; int leaf;
                 if (COUNT) ++n_tris;
-                if (tri_fetch_test(S, i, r, r.T0, t, u, v, leaf) && t <= best) {
+                if (tri_fetch_test(S, i, r, r.T0, t, u, v, leaf)) {
                     if (t < best) {
+                        second = best;
                         best = t; out.t = t; out.tri = i; out.u = u; out.v = v; tie = false; best_leaf = leaf;
                         cull = cull_after_hit(S, r, t);
-                    } else {
+                    } else if (t == best) {
                         tie = true;
+                    } else {
+                        second = fminf(second, t);
                     }
                 }
             }
@@ -100,8 +107,7 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
     }
     if (out.tri < 0) return true;
     if (tie) return false;
-    // certify: the winner's reference leaf must still be visible with ray.tMax == t
-    return leaf_visible(S, best_leaf, r, out.t);
+    return certify_unique(S, r, best, best_leaf, second);
 }
 
 // ---- occlusion query -------------------------------------------------------------------------------

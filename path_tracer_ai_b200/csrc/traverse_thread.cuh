@@ -35,6 +35,7 @@ struct LaneState {
     RayQ r;
     HitRec best;
     int best_leaf;
+    float second;          // smallest t among the other candidates seen (certify_unique)
     float cull;
     int sp;
     uint32_t cur;          // inner wide node to expand (valid when tri_next == tri_end)
@@ -52,6 +53,7 @@ __device__ __forceinline__ bool lane_begin(const DeviceScene& S, LaneState& st, 
     st.r = r;
     st.best.t = B2PT_INF; st.best.tri = -1; st.best.u = 0.0f; st.best.v = 0.0f;
     st.best_leaf = -1;
+    st.second = B2PT_INF;
     st.cull = r.T0;
     st.sp = 0;
     st.cur = 0;
@@ -69,10 +71,13 @@ __device__ __forceinline__ bool lane_begin(const DeviceScene& S, LaneState& st, 
             if (tri_fetch_test(S, i, r, r.T0, t, u, v, leaf)) {
                 if (ANY) return true;
                 if (t < st.best.t) {
+                    st.second = st.best.t;
                     st.best.t = t; st.best.tri = i; st.best.u = u; st.best.v = v; st.tie = false; st.best_leaf = leaf;
                     st.cull = cull_after_hit(S, r, t);
                 } else if (t == st.best.t) {
                     st.tie = true;
+                } else {
+                    st.second = fminf(st.second, t);
                 }
             }
         }
@@ -143,12 +148,15 @@ __device__ __forceinline__ bool lane_closest_step(const DeviceScene& S, LaneStat
                 float t, u, v; int leaf;
                 if (COUNT) ++n_tris;
                 int i = st.tri_next++;
-                if (tri_fetch_test(S, i, st.r, st.r.T0, t, u, v, leaf) && t <= st.best.t) {
+                if (tri_fetch_test(S, i, st.r, st.r.T0, t, u, v, leaf)) {
                     if (t < st.best.t) {
+                        st.second = st.best.t;
                         st.best.t = t; st.best.tri = i; st.best.u = u; st.best.v = v; st.tie = false; st.best_leaf = leaf;
                         st.cull = cull_after_hit(S, st.r, t);
-                    } else {
+                    } else if (t == st.best.t) {
                         st.tie = true;
+                    } else {
+                        st.second = fminf(st.second, t);
                     }
                 }
             }
@@ -166,7 +174,7 @@ __device__ __forceinline__ bool lane_certify(const DeviceScene& S, const LaneSta
     if (st.overflow) return false;
     if (st.best.tri < 0) return true;
     if (st.tie) return false;
-    return leaf_visible(S, st.best_leaf, st.r, st.best.t);
+    return certify_unique(S, st.r, st.best.t, st.best_leaf, st.second);
 }
 
 // One bounded step of an occlusion query.  Returns 0 = keep going, 1 = finished & occluded, 2 = finished

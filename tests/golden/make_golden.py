@@ -12,8 +12,9 @@ Outputs (small, committed):
                       (float framebuffer) + the scene arrays (pre-build order) so that tests do not
                       depend on OBJ parsing.
   render_mesh.npz     reference Renderer::render of a 6,000-triangle tessellated mesh scene (displaced terrain, tori,
-                      spheres: diffuse, MIRROR, rough specular, GLASS, smooth normals), 32x18, 6 bounces, as four independent
-                      runs of 65536 spp (their mean = a 262144-spp frame; their scatter = the reference's own noise).
+                      spheres: diffuse, MIRROR, rough specular, GLASS, smooth normals), 32x18, 6 bounces: the float64 mean of 64
+                      independent single-threaded 16384-spp frames (1M spp; render_mesh_golden says why one thread and why
+                      frames of 16384) and the means of its four quarters (the reference's own remaining noise).
                       The scene generator's roughness-0.1 object is set to 0.35: the reference's SPECULAR direct term is
                       albedo * D_GGX with no normalisation (renderer.hpp:286-290), peak 1/(pi r^4) = 3183 at r = 0.1, and
                       two 16384-spp runs of the REFERENCE ITSELF then differ by 57-81 % relRMSE per channel and 2.2 % in mean
@@ -49,22 +50,53 @@ def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-def render_mesh_golden():
+def _mesh_scene():
     ms = scenes.mesh_scene(6000, seed=11)
     m8 = ms["materials8"].copy()
     m8[5, 4] = 0.35
+    return ms, m8
+
+
+def _mesh_worker(nruns):
+    """nruns sequential single-threaded reference frames (own process, own RefOracle); returns their float64 sum."""
+    ms, m8 = _mesh_scene()
     R = RefOracle(ms["pos"], ms["nrm"], ms["mat"], m8)
-    # four INDEPENDENT runs of 65536 spp (the reference seeds itself from std::random_device): their mean is the
-    # 262144-spp golden, their scatter says how far the reference is from ITSELF pixel by pixel
-    W, H, SPP, B, RUNS = 32, 18, 65536, 6, 4
-    runs, secs = [], 0.0
-    for _ in range(RUNS):
-        fb, s1 = R.render(W, H, SPP, B)
-        runs.append(fb); secs += s1
-    runs = np.stack(runs)
+    acc = np.zeros((MESH_H, MESH_W, 3), np.float64)
+    for _ in range(nruns):
+        acc += R.render(MESH_W, MESH_H, MESH_SPP, MESH_B, nthreads=1)[0]
+    return acc
+
+
+MESH_W, MESH_H, MESH_SPP, MESH_B, MESH_GROUPS, MESH_RUNS_PER_GROUP = 32, 18, 16384, 6, 4, 16
+
+
+def render_mesh_golden():
+    # 64 INDEPENDENT reference frames of 16384 spp, each by Renderer::render on ONE thread, averaged in float64.
+    #  * one thread: render() draws tracePath's random numbers from the Renderer's member mt19937, which its OpenMP
+    #    loop shares between threads without synchronisation (renderer.hpp:53, :128-130) — a multi-threaded frame is
+    #    the reference with a raced generator (duplicated / skipped / out-of-range state reads), not a clean target;
+    #  * 16384 spp per frame: render() adds samples in fp32 (renderer.hpp:73); beyond ~10^5 samples the running sum's ulp
+    #    reaches the size of a typical sample and the pixel mean drifts (on this scene's highlight pixel the fp32 mean of
+    #    4M samples is 1 % below the float64 mean of the same estimator), so a converged target is an AVERAGE OF FRAMES.
+    # Stored: the mean of all frames (fb_ref, 1,048,576 spp) and the four group means (fb_runs, 262144 spp each): their
+    # scatter is the reference's own remaining noise.
+    import multiprocessing as mp
+    import time
+    ms, m8 = _mesh_scene()
+    R = RefOracle(ms["pos"], ms["nrm"], ms["mat"], m8)
+    workers = min(mp.cpu_count(), MESH_GROUPS * MESH_RUNS_PER_GROUP)
+    per = MESH_GROUPS * MESH_RUNS_PER_GROUP // workers
+    assert per * workers == MESH_GROUPS * MESH_RUNS_PER_GROUP and workers % MESH_GROUPS == 0
+    t0 = time.time()
+    with mp.get_context("spawn").Pool(workers) as pool:
+        sums = pool.map(_mesh_worker, [per] * workers)
+    secs = time.time() - t0
+    g = workers // MESH_GROUPS
+    runs = np.stack([sum(sums[k * g:(k + 1) * g]) / (g * per) for k in range(MESH_GROUPS)])
     np.savez_compressed(os.path.join(HERE, "render_mesh.npz"), pos=ms["pos"], nrm=ms["nrm"], mat=ms["mat"], order=R.order(),
-                        materials8=m8, fb_ref=runs.mean(0), fb_runs=runs, spp=SPP * RUNS, bounces=B)
-    print(f"render_mesh: {RUNS} x {W}x{H}x{SPP} in {secs:.1f}s mean {runs.mean():.5f}")
+                        materials8=m8, fb_ref=runs.mean(0).astype(np.float32), fb_runs=runs.astype(np.float32),
+                        spp=MESH_SPP * MESH_GROUPS * MESH_RUNS_PER_GROUP, frame_spp=MESH_SPP, bounces=MESH_B)
+    print(f"render_mesh: {MESH_GROUPS * MESH_RUNS_PER_GROUP} x {MESH_W}x{MESH_H}x{MESH_SPP} in {secs:.1f}s mean {runs.mean():.5f}")
 
 
 def render_c1_golden():

@@ -168,18 +168,32 @@ def test_converged_render_matches_reference_golden(engine):
 
 
 def test_converged_mesh_scene_matches_reference_golden(engine):
-    """The same gate on a tessellated mesh scene with smooth normals and all three material types — diffuse, MIRROR,
-    rough specular, GLASS (golden: the reference itself at 262144 spp, 32x18, 6 bounces; tests/golden/make_golden.py
-    says why the roughness-0.1 object of the generator is set to 0.35)."""
+    """The statistical gate on a tessellated mesh scene with smooth normals and all three material types — diffuse,
+    MIRROR, rough specular, GLASS.  Golden: the float64 mean of 64 independent single-threaded 16384-spp frames of the
+    reference itself (1M spp, 32x18, 6 bounces; tests/golden/make_golden.py says why single-threaded, why frames of
+    16384 spp and why the generator's roughness-0.1 object is set to 0.35).  The GPU side is the same estimator: the
+    float64 mean of 128 frames of 16384 spp with different seeds (2M spp) — one fp32-accumulated frame of 2M spp would
+    sit 1 % below its own expectation on the highlight pixel (fp32 sums stop resolving the samples, in the reference
+    just as here).  Tolerance: BASELINE.json's north star, relRMSE < 1 % per channel and mean luminance within 0.5 %;
+    measured 0.3-0.4 %, the reference's own two halves differ by 0.4-0.5 %."""
     g = np.load(os.path.join(GOLD, "render_mesh.npz"))
     order = pt.reference_order(g["pos"])
     assert np.array_equal(order, g["order"])
     engine.upload_scene(g["pos"][order], g["nrm"][order], g["mat"][order], g["materials8"])
-    ref = g["fb_ref"]
+    ref, runs = g["fb_ref"].astype(np.float64), g["fb_runs"].astype(np.float64)
     H, W, _ = ref.shape
-    fb = engine.render(pt.Camera().c, W, H, 1 << 21, int(g["bounces"]), seed=77)
-    rel = np.sqrt(((fb - ref) ** 2).mean(axis=(0, 1))) / ref.mean(axis=(0, 1))
-    assert (rel < 0.01).all(), rel                       # tolerance stated by BASELINE.json north_star
+    frames, spp = 128, int(g["frame_spp"])
+    acc = np.zeros((H, W, 3), np.float64)
+    for k in range(frames):
+        acc += engine.render(pt.Camera().c, W, H, spp, int(g["bounces"]), seed=7700 + k)
+    fb = acc / frames
+
+    def rel(x, y):
+        return np.sqrt(((x - y) ** 2).mean(axis=(0, 1))) / y.mean(axis=(0, 1))
+
+    halves = rel(runs[:2].mean(0), runs[2:].mean(0))
+    assert (rel(fb, ref) < 0.01).all(), (rel(fb, ref), halves)      # tolerance stated by BASELINE.json north_star
+    assert (rel(fb, ref) < 2.0 * halves).all(), (rel(fb, ref), halves)   # and no further from the reference than it is from itself
     assert abs(lum(fb).mean() / lum(ref).mean() - 1) < 0.005
 
 

@@ -9,7 +9,7 @@ ap = argparse.ArgumentParser(add_help=False)
 ap.add_argument("--scene", default="cornell"); ap.add_argument("--tris", type=int, default=1_000_000)
 ap.add_argument("-w", type=int, default=1920); ap.add_argument("-h", type=int, default=1080)
 ap.add_argument("-s", type=int, default=16); ap.add_argument("-b", type=int, default=5); ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--max-paths", type=int, default=8 << 20); ap.add_argument("--tag", default=""); ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--max-paths", type=int, default=8 << 20); ap.add_argument("--tag", default=""); ap.add_argument("--flags", type=int, default=0); ap.add_argument("--seed", type=int, default=1)
 a = ap.parse_args()
 sc = pt.Scene()
 if a.scene == "cornell":
@@ -18,7 +18,7 @@ if a.scene == "cornell":
 else:
     ms = scenes.mesh_scene(a.tris, seed=1234)
     sc.setContents(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
-eng = pt.Engine(max_paths=a.max_paths)
+eng = pt.Engine(max_paths=a.max_paths, flags=a.flags)
 eng.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
 d_rgb = torch.empty(a.w * a.h * 3, dtype=torch.float32, device="cuda:0")
 torch.cuda.synchronize()
