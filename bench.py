@@ -417,7 +417,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     agg = {"extend_rays": 0, "shadow_rays": 0, "samples": 0, "kernel_launches": 0, "gpu_seconds": 0.0, "extend_seconds": 0.0,
-           "shadow_seconds": 0.0, "extend_launches": 0, "shadow_launches": 0, "fallback_rays": 0}
+           "shadow_seconds": 0.0, "order_seconds": 0.0, "extend_launches": 0, "shadow_launches": 0, "fallback_rays": 0}
     for _ in range(args.steps):
         st = step_device()
         for k in agg:
@@ -502,8 +502,8 @@ def main():
     nodes_per_ray = cst["node_fetches"] / max(nrays_c, 1)
     tris_per_ray = cst["tri_fetches"] / max(nrays_c, 1)
     shadow_dominant = agg["shadow_seconds"] >= agg["extend_seconds"]
-    # shadow rays: k_shadow_rtc at depth 0 (coherent), k_shadow_pool on the bounces; closest hit: k_extend_rtc
-    dominant = "k_shadow_pool" if shadow_dominant else "k_extend_rtc"
+    # every bounce is in hit-point order, so both ray kinds take the run-to-completion kernels (engine default flags)
+    dominant = "k_shadow_rtc" if shadow_dominant else "k_extend_rtc"
     if shadow_dominant:
         # per shadow ray: read the queue entry (4 B) and the vertex it shares with the other lights
         # (g0+g1 = 32 B / nlight), write the visibility byte
@@ -562,6 +562,7 @@ def main():
         "config": config_dict(args, world, len(sc.pos)),
         "mrays_per_s": rays / wall * 1e-6, "rays_per_sample": rays / samples, "device_ms_per_step": 1e3 * dev_s / args.steps,
         "extend_ms_per_step": 1e3 * agg["extend_seconds"] / args.steps, "shadow_ms_per_step": 1e3 * agg["shadow_seconds"] / args.steps,
+        "order_ms_per_step": 1e3 * agg["order_seconds"] / args.steps,
         "extend_mrays_per_s": agg["extend_rays"] / max(agg["extend_seconds"], 1e-12) * 1e-6,
         "shadow_mrays_per_s": agg["shadow_rays"] / max(agg["shadow_seconds"], 1e-12) * 1e-6,
         "fallback_rays_per_step": agg["fallback_rays"] / args.steps, "build_ms": 1e3 * build_s,

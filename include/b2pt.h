@@ -108,10 +108,11 @@ typedef struct b2pt_stats {
     double gpu_seconds;       /* CUDA-event time of the call's device work */
     double trace_seconds;     /* CUDA-event time spent in extend + shadow traversal kernels */
     double build_seconds;     /* (upload) acceleration-structure build, device time */
-    double extend_seconds;    /* part of trace_seconds spent in closest-hit kernels (incl. exact fallback) */
+    double extend_seconds;    /* part of trace_seconds spent in closest-hit kernels (renderer: the k_extend_* launches alone) */
     double shadow_seconds;    /* part of trace_seconds spent in the direct-light / any-hit kernels */
     int64_t extend_launches;  /* closest-hit kernel launches (fast kernel only) */
     int64_t shadow_launches;  /* direct-light / any-hit kernel launches */
+    double order_seconds;     /* renderer: between closest hit and shadow rays of every bounce — exact fallback, hit-point sort, k_hitinfo */
 } b2pt_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------- */

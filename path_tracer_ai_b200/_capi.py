@@ -54,7 +54,7 @@ class Stats(C.Structure):
                 ("fallback_rays", C.c_int64), ("node_fetches", C.c_int64), ("tri_fetches", C.c_int64),
                 ("kernel_launches", C.c_int64), ("gpu_seconds", C.c_double), ("trace_seconds", C.c_double),
                 ("build_seconds", C.c_double), ("extend_seconds", C.c_double), ("shadow_seconds", C.c_double),
-                ("extend_launches", C.c_int64), ("shadow_launches", C.c_int64)]
+                ("extend_launches", C.c_int64), ("shadow_launches", C.c_int64), ("order_seconds", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

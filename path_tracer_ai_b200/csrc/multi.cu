@@ -170,7 +170,7 @@ int b2pt_multi_render(b2pt_multi* m, const b2pt_camera* cam, const b2pt_settings
         s.extend_launches += t.extend_launches; s.shadow_launches += t.shadow_launches;
         s.gpu_seconds = std::max(s.gpu_seconds, t.gpu_seconds); s.trace_seconds = std::max(s.trace_seconds, t.trace_seconds);
         s.build_seconds = std::max(s.build_seconds, t.build_seconds); s.extend_seconds = std::max(s.extend_seconds, t.extend_seconds);
-        s.shadow_seconds = std::max(s.shadow_seconds, t.shadow_seconds);
+        s.shadow_seconds = std::max(s.shadow_seconds, t.shadow_seconds); s.order_seconds = std::max(s.order_seconds, t.order_seconds);
     }
     if (n > 1) s.kernel_launches += 1;
     m->stats = s;

@@ -147,24 +147,7 @@ __device__ __forceinline__ Epilogue hit_epilogue(const DeviceScene& S, const Wav
 #define B2PT_BIN_BLOCK 256
 #define B2PT_BIN_WARPS (B2PT_BIN_BLOCK / 32)
 
-__device__ __forceinline__ void block_append(int* counter, int* queue, bool pred, int value) {
-    __shared__ int s_w[B2PT_BIN_WARPS];
-    __shared__ int s_base;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned b = __ballot_sync(0xffffffffu, pred);
-    if (lane == 0) s_w[w] = __popc(b);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-#pragma unroll
-        for (int i = 0; i < B2PT_BIN_WARPS; ++i) { int t = s_w[i]; s_w[i] = tot; tot += t; }
-        s_base = tot ? atomicAdd(counter, tot) : 0;
-    }
-    __syncthreads();
-    if (pred) queue[s_base + s_w[w] + __popc(b & ((1u << lane) - 1u))] = value;
-}
-
-// The same append with the block's entries grouped by `bin` (0..7, -1 = nothing to append): k_shade groups the next
+// Append with the block's entries grouped by `bin` (0..7, -1 = nothing to append): k_shade groups the next
 // rays of its 256 neighbouring vertices by direction octant, so a warp of the next closest-hit launch holds rays that
 // start close together AND head the same way.
 __device__ __forceinline__ void block_append_binned(int* counter, int* queue, int bin, int value) {
@@ -240,6 +223,37 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
     }
 }
 
+// ---- hit-point order --------------------------------------------------------------------------------------------------
+// From the first bounce on the paths of a batch hit the scene all over the place, and queue neighbours (neighbouring
+// pixels) stop being spatial neighbours: the shadow rays and the next bounce rays of a warp then start in 32 unrelated
+// corners of the tree.  Before k_hitinfo bins a bounce, its paths are therefore put in the Morton order of their hit
+// points (one radix sort of (key, path slot) pairs per bounce, the pairs written by the closest-hit kernel itself; the
+// camera rays' hits too — a 3D-compact block of vertices beats a scanline run of pixels): a block of k_hitinfo then holds 256 neighbouring
+// vertices, its light-major shadow entries are 32 near-identical rays per warp, and k_shade appends the next rays in
+// the same order, so the next closest-hit launch reads origin-sorted rays.  The key is only an ORDER (computed with an
+// FMA, quantised to 1024^3 cells of the scene's coordinate range): no result depends on it — every path's arithmetic
+// is a function of its own state and k_resolve adds samples in sample order.
+// Key: 32-bit Morton code, 11 + 11 + 10 bits (x, y: 2048 cells, z: 1024 cells over the scene's coordinate range), all
+// of it sorted (four 8-bit radix passes).  Coarser orders are cheaper to sort and cost more than they save: on one
+// 32M-path batch of the 1M-triangle scene the shadow launches take 42.1 / 37.7 / 33.3 / 29.5 ms with 16 / 20 / 24 / 30
+// key bits.
+__device__ __forceinline__ uint32_t morton_spread11(uint32_t v) {   // bit i -> bit 3i, i < 11
+    v &= 0x7FFu;
+    v = (v | (v << 16)) & 0x070000FFu;
+    v = (v | (v << 8)) & 0x0700F00Fu;
+    v = (v | (v << 4)) & 0x430C30C3u;
+    v = (v | (v << 2)) & 0x49249249u;
+    return v;
+}
+// Morton key of the hit point o + t d (misses: the largest key).
+__device__ __forceinline__ uint32_t hit_point_key(V3 o, V3 d, const HitRec& h, float bound) {
+    if (h.tri < 0) return 0xFFFFFFFFu;
+    const float sc = 1024.0f / bound;
+    const float x = fmaf(fmaf(d.x, h.t, o.x), sc, 1024.0f), y = fmaf(fmaf(d.y, h.t, o.y), sc, 1024.0f), z = fmaf(fmaf(d.z, h.t, o.z), 0.5f * sc, 512.0f);
+    const uint32_t xi = (uint32_t)fminf(fmaxf(x, 0.0f), 2047.0f), yi = (uint32_t)fminf(fmaxf(y, 0.0f), 2047.0f), zi = (uint32_t)fminf(fmaxf(z, 0.0f), 1023.0f);
+    return morton_spread11(xi) | (morton_spread11(yi) << 1) | (morton_spread11(zi) << 2);
+}
+
 // block sizes of the two run-to-completion traversal kernels (64 / 128 / 256 measured: profiles/r01_experiments.md)
 #ifndef B2PT_EXT_BLOCK
 #define B2PT_EXT_BLOCK 128
@@ -253,6 +267,9 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
 #ifndef B2PT_EXT_MINB
 #define B2PT_EXT_MINB 10
 #endif
+#ifndef B2PT_SHD_MINB
+#define B2PT_SHD_MINB 10   // 48 registers (64 without a bound): sorted 1M-triangle batch 35.0 -> 33.3 ms of shadow rays
+#endif
 // Closest hit for the active paths (traverse_rtc.cuh): one thread per queue entry.
 // With FUSED the kernel also runs the per-vertex epilogue of its certified rays (hit point, shading normal,
 // material, light culling, binning — hit_epilogue + bin_path): the hit record never goes through HBM and the
@@ -263,7 +280,7 @@ __device__ __forceinline__ void bin_path(const Wave& W, const Epilogue& e, int p
 // trees.
 template <bool COUNT, bool FUSED>
 __global__ void __launch_bounds__(FUSED ? B2PT_EXT_BLOCK_FUSED : B2PT_EXT_BLOCK, (B2PT_EXT_MINB * 128) / (FUSED ? B2PT_EXT_BLOCK_FUSED : B2PT_EXT_BLOCK)) k_extend_rtc(DeviceScene S, Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr,
-                                                    int P, TraceCounters* __restrict__ tc) {
+                                                    int P, TraceCounters* __restrict__ tc, uint32_t* __restrict__ order_keys, int* __restrict__ order_vals) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int total = list ? *count_ptr : P;
     if (blockIdx.x * blockDim.x >= total) return;   // whole block beyond the queue (uniform)
@@ -276,8 +293,11 @@ __global__ void __launch_bounds__(FUSED ? B2PT_EXT_BLOCK_FUSED : B2PT_EXT_BLOCK,
         RayQ r = make_rayq_normalised(f4v(o4), f4v(d4), B2PT_INF);
         HitRec h;
         bool ok = closest_rtc<COUNT>(S, r, h, n_nodes, n_tris);
-        if (!FUSED) W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
-        else if (ok) e = hit_epilogue(S, W, p, r.o, r.d, h);
+        if (!FUSED) {
+            W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+            // (key, slot) pair of the hit-point order; an uncertified ray's key comes from its provisional hit — only an order
+            if (order_keys) { order_keys[k] = hit_point_key(r.o, r.d, h, S.coord_bound); order_vals[k] = p; }
+        } else if (ok) e = hit_epilogue(S, W, p, r.o, r.d, h);
         if (!ok) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
     }
     if (FUSED) bin_path<B2PT_EXT_BLOCK_FUSED / 32>(W, e, p, S.nlight);
@@ -291,7 +311,7 @@ __global__ void __launch_bounds__(FUSED ? B2PT_EXT_BLOCK_FUSED : B2PT_EXT_BLOCK,
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(B2PT_SHD_BLOCK) k_shadow_rtc(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
+__global__ void __launch_bounds__(B2PT_SHD_BLOCK, B2PT_SHD_MINB) k_shadow_rtc(DeviceScene S, Wave W, TraceCounters* __restrict__ tc) {
     const int nl = S.nlight;
     const int total = W.counters[C_SHADOW];
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -410,50 +430,6 @@ __global__ void __launch_bounds__(128) k_extend_fallback(DeviceScene S, Wave W) 
                 if ((e.lights >> l) & 1u) W.q_shadow[atomicAdd(&W.counters[C_SHADOW], 1)] = p * S.nlight + l;
         }
     }
-}
-
-// ---- hit-point order --------------------------------------------------------------------------------------------------
-// From the first bounce on the paths of a batch hit the scene all over the place, and queue neighbours (neighbouring
-// pixels) stop being spatial neighbours: the shadow rays and the next bounce rays of a warp then start in 32 unrelated
-// corners of the tree.  Before k_hitinfo bins a bounce, its paths are therefore put in the Morton order of their hit
-// points (one radix sort of (key, path slot) pairs per bounce; the camera rays' hits too — a 3D-compact block of
-// vertices beats a scanline run of pixels: depth-0 shadow launch 18.6 -> ms at 32M paths): a block of k_hitinfo then holds 256 neighbouring
-// vertices, its light-major shadow entries are 32 near-identical rays per warp, and k_shade appends the next rays in
-// the same order, so the next closest-hit launch reads origin-sorted rays.  The key is only an ORDER (computed with an
-// FMA, quantised to 1024^3 cells of the scene's coordinate range): no result depends on it — every path's arithmetic
-// is a function of its own state and k_resolve adds samples in sample order.
-#ifndef B2PT_SORT_BEGIN_BIT
-#define B2PT_SORT_BEGIN_BIT 6     // the 24 high bits of the 30-bit Morton code: three 8-bit radix passes, 256^3 cells
-#endif
-__device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
-    v &= 1023u;
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-// keys[k] / vals[k] for k < P: entry k of the active queue (slot, Morton key of its hit point); misses and the tail
-// beyond the queue get the largest key.  The sort is stable, so the first *count_ptr sorted entries are the queue's.
-__global__ void __launch_bounds__(256) k_sort_keys(Wave W, const int* __restrict__ list, const int* __restrict__ count_ptr, int P,
-                                                    float bound, uint32_t* __restrict__ keys, int* __restrict__ vals) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= P) return;
-    const int total = list ? *count_ptr : P;
-    uint32_t key = 0x3FFFFFFFu;
-    int p = -1;
-    if (k < total) {
-        p = list ? list[k] : k;
-        float4 h = W.hit[p];
-        if (__float_as_int(h.y) >= 0) {
-            float4 o = W.ro[p], d = W.rd[p];
-            const float sc = 512.0f / bound;
-            float x = fmaf(fmaf(d.x, h.x, o.x), sc, 512.0f), y = fmaf(fmaf(d.y, h.x, o.y), sc, 512.0f), z = fmaf(fmaf(d.z, h.x, o.z), sc, 512.0f);
-            uint32_t xi = (uint32_t)fminf(fmaxf(x, 0.0f), 1023.0f), yi = (uint32_t)fminf(fmaxf(y, 0.0f), 1023.0f), zi = (uint32_t)fminf(fmaxf(z, 0.0f), 1023.0f);
-            key = morton_spread10(xi) | (morton_spread10(yi) << 1) | (morton_spread10(zi) << 2);
-        }
-    }
-    keys[k] = key; vals[k] = p;
 }
 
 // Hit record -> hit point / shading normal / material, and the one-pass counting sort by material type.
@@ -792,7 +768,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     const bool count = (ctx->flags & B2PT_FLAG_COUNT_FETCHES) != 0;
     // closest-hit kernel with the per-vertex epilogue fused in: small trees only (see k_extend_rtc)
     const bool fused = S.nwide <= 64;
-    // hit-point order of the bounces (k_sort_keys): scenes whose rays diverge, i.e. the ones that do not fuse
+    // hit-point order of the bounces (hit_point_key): scenes whose rays diverge, i.e. the ones that do not fuse
     const bool sort_hits = !fused && !(ctx->flags & B2PT_FLAG_NO_SORT);
     uint32_t *sort_keys[2] = {nullptr, nullptr};
     int* sort_vals[2] = {nullptr, nullptr};
@@ -803,12 +779,13 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
         if ((rc = scratch_reserve(ctx, 13, 4 * qi, &sb_))) return rc;
         sort_keys[0] = (uint32_t*)sb_; sort_keys[1] = sort_keys[0] + Pmax; sort_vals[0] = (int*)(sort_keys[1] + Pmax); sort_vals[1] = sort_vals[0] + Pmax;
         B2PT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, sort_temp_bytes, sort_keys[0], sort_keys[1], sort_vals[0], sort_vals[1], (int)Pmax,
-                                                       B2PT_SORT_BEGIN_BIT, 30, stream));
+                                                       0, 32, stream));   // sized for any bit range
         if ((rc = scratch_reserve(ctx, 14, sort_temp_bytes + 16, &sort_temp))) return rc;
     }
     int64_t launches = 0, n_extend = 0, n_shadow = 0;
-    float extend_ms = 0.0f, shadow_ms = 0.0f;
-    // Traversal time is measured with events around extend + direct of every bounce; they come from a pool owned by
+    float extend_ms = 0.0f, order_ms = 0.0f, shadow_ms = 0.0f;
+    // Traversal time is measured with events around the closest-hit launch, the ordering / epilogue stage and the shadow
+    // launch of every bounce; they come from a pool owned by
     // the context (created once, reused by every frame) and are read after the frame's single synchronisation.
     size_t ev_used = 0;
     auto ev = [&]() {
@@ -862,31 +839,29 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                     if (count) k_extend_pool<true><<<pgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                     else k_extend_pool<false><<<pgrid, B2PT_PBLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
                 } else if (fused) {
-                    if (count) k_extend_rtc<true, true><<<(A + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    else k_extend_rtc<false, true><<<(A + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    if (count) k_extend_rtc<true, true><<<(A + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters, nullptr, nullptr);
+                    else k_extend_rtc<false, true><<<(A + B2PT_EXT_BLOCK_FUSED - 1) / B2PT_EXT_BLOCK_FUSED, B2PT_EXT_BLOCK_FUSED, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters, nullptr, nullptr);
                 } else {
-                    if (count) k_extend_rtc<true, false><<<(A + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
-                    else k_extend_rtc<false, false><<<(A + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters);
+                    if (count) k_extend_rtc<true, false><<<(A + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters, sort_keys[0], sort_vals[0]);
+                    else k_extend_rtc<false, false><<<(A + B2PT_EXT_BLOCK - 1) / B2PT_EXT_BLOCK, B2PT_EXT_BLOCK, 0, stream>>>(S, Wv, list, &Wv.counters[cur], P, ctx->d_counters, sort_keys[0], sort_vals[0]);
                 }
                 dbg("k_extend", pix_begin, sb, depth);
+                ev();
                 if (fused) {   // k_extend_rtc has already run the epilogue of its certified rays
                     k_extend_fallback<true><<<ctx->sm_count * 4, 128, 0, stream>>>(S, Wv);
                     dbg("k_extend_fallback", pix_begin, sb, depth);
                 } else if (sort_hits) {
                     // The exact recursion of the handful of uncertified rays (a fraction of a millisecond of pure latency) runs
-                    // on the side stream while this one sorts the bounce; k_sort_keys may read a hit record the recursion is
-                    // about to replace — the key is only an order.
+                    // on the side stream while this one sorts the bounce (their keys come from the provisional hits: only an order).
                     B2PT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, stream));
                     B2PT_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
                     k_extend_fallback<false><<<ctx->sm_count * 4, 128, 0, ctx->side>>>(S, Wv);
                     B2PT_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
                     ++launches;
-                    k_sort_keys<<<(A + 255) / 256, 256, 0, stream>>>(Wv, list, &Wv.counters[cur], A, S.coord_bound, sort_keys[0], sort_vals[0]);
-                    dbg("k_sort_keys", pix_begin, sb, depth);
                     size_t tb = sort_temp_bytes;
                     B2PT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_temp, tb, sort_keys[0], sort_keys[1], sort_vals[0], sort_vals[1], A,
-                                                                   B2PT_SORT_BEGIN_BIT, 30, stream));
-                    launches += 4;   // histogram + three onesweep passes
+                                                                   0, 32, stream));
+                    launches += 5;   // histogram + four onesweep passes
                     B2PT_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_join, 0));
                     k_hitinfo<<<(A + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, sort_vals[1], &Wv.counters[cur], P);
                     dbg("k_hitinfo", pix_begin, sb, depth);
@@ -932,10 +907,11 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     unsigned long long totals[3] = {0, 0, 0};
     cudaError_t ce = cudaMemcpyAsync(totals, Wv.totals, sizeof(totals), cudaMemcpyDeviceToHost, stream);
     cudaError_t se = cudaStreamSynchronize(stream);
-    for (size_t i = 0; i + 2 < ev_used; i += 3) {   // per bounce: before extend, after extend, after direct
+    for (size_t i = 0; i + 3 < ev_used; i += 4) {   // per bounce: before extend, after extend, after the epilogue, after direct
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) extend_ms += ms;
-        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i + 1], ctx->ev_pool[i + 2]) == cudaSuccess) shadow_ms += ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i + 1], ctx->ev_pool[i + 2]) == cudaSuccess) order_ms += ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i + 2], ctx->ev_pool[i + 3]) == cudaSuccess) shadow_ms += ms;
     }
     if (!dbg_fault.empty()) { ctx->err = "render kernel fault: " + dbg_fault; return B2PT_ERR_CUDA; }
     if (le != cudaSuccess) { cuda_fail(ctx, le, "render kernels", __FILE__, __LINE__); return B2PT_ERR_CUDA; }
@@ -947,6 +923,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
     ctx->stats.kernel_launches = launches;
     ctx->stats.extend_seconds = extend_ms * 1e-3;
     ctx->stats.shadow_seconds = shadow_ms * 1e-3;
+    ctx->stats.order_seconds = order_ms * 1e-3;
     ctx->stats.trace_seconds = (extend_ms + shadow_ms) * 1e-3;
     ctx->stats.extend_launches = n_extend;
     ctx->stats.shadow_launches = n_shadow;

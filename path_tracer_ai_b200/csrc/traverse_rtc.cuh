@@ -81,20 +81,21 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
             }
         } else {
             int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;
+            auto accept = [&](int i, float t, float u, float v, int leaf) {
+                if (t < best) {
+                    second = best;
+                    best = t; out.t = t; out.tri = i; out.u = u; out.v = v; tie = false; best_leaf = leaf;
+                    cull = cull_after_hit(S, r, t);
+                } else if (t == best) {
+                    tie = true;
+                } else {
+                    second = fminf(second, t);
+                }
+            };
             for (int i = first; i < first + cnt; ++i) {
                 float t, u, v; int leaf;
                 if (COUNT) ++n_tris;
-                if (tri_fetch_test(S, i, r, r.T0, t, u, v, leaf)) {
-                    if (t < best) {
-                        second = best;
-                        best = t; out.t = t; out.tri = i; out.u = u; out.v = v; tie = false; best_leaf = leaf;
-                        cull = cull_after_hit(S, r, t);
-                    } else if (t == best) {
-                        tie = true;
-                    } else {
-                        second = fminf(second, t);
-                    }
-                }
+                if (tri_fetch_test(S, i, r, r.T0, t, u, v, leaf)) accept(i, t, u, v, leaf);
             }
         }
         // pop

@@ -31,7 +31,7 @@ for r in range(a.reps + 1):
 rays = best["extend_rays"] + best["shadow_rays"]
 print(json.dumps(dict(tag=a.tag, scene=a.scene, tris=len(sc.pos), msamples_s=round(best["samples"] / best["gpu_seconds"] * 1e-6, 1),
                       mrays_s=round(rays / best["gpu_seconds"] * 1e-6, 1), ms=round(best["gpu_seconds"] * 1e3, 1),
-                      extend_ms=round(best["extend_seconds"] * 1e3, 1), shadow_ms=round(best["shadow_seconds"] * 1e3, 1),
+                      extend_ms=round(best["extend_seconds"] * 1e3, 1), order_ms=round(best["order_seconds"] * 1e3, 1), shadow_ms=round(best["shadow_seconds"] * 1e3, 1),
                       extend_mrays_s=round(best["extend_rays"] / best["extend_seconds"] * 1e-6, 1),
                       shadow_mrays_s=round(best["shadow_rays"] / max(best["shadow_seconds"], 1e-9) * 1e-6, 1),
                       rays_per_sample=round(rays / best["samples"], 2), fallback=best["fallback_rays"], mean=float(d_rgb.mean()))))
