@@ -55,7 +55,7 @@ WORKLOADS = {
     "c3": (1920, 1080, 256, 8, 1_000_000, "BASELINE configs[2]: 1M-triangle mesh scene 1920x1080 256 spp 8 bounces"),
     "c5": (3840, 2160, 1024, 8, 10_000_000, "BASELINE configs[4]: 10M-triangle dielectric-heavy scene 3840x2160 1024 spp 8 bounces"),
 }
-DEFAULT_MAX_PATHS = 32 << 20
+DEFAULT_MAX_PATHS = 64 << 20
 TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_traffic.json")
 KERNEL_SOURCES = ["exact.cuh", "ctx.cuh", "traverse.cuh", "traverse_rtc.cuh", "traverse_thread.cuh", "traverse_pool.cuh", "render.cu", "trace.cu", "build.cu"]
 

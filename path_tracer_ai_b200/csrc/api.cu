@@ -100,7 +100,7 @@ int b2pt_create(const b2pt_config* cfg, b2pt_ctx** out) {
     ctx->learn_order = (ctx->flags & B2PT_FLAG_NO_LEARN_ORDER) == 0;
     ctx->debug_sync = std::getenv("B2PT_DEBUG_SYNC") != nullptr;   // read once, here
     ctx->sm_count = prop.multiProcessorCount;
-    ctx->max_paths = (cfg && cfg->max_paths_in_flight > 0) ? cfg->max_paths_in_flight : (int64_t)(16 << 20);   // larger wavefronts amortise the kernels' tails: 1M-triangle render 150 (2M) / 185 (8M) / 194 (16M) Msamples/s
+    ctx->max_paths = (cfg && cfg->max_paths_in_flight > 0) ? cfg->max_paths_in_flight : (int64_t)(32 << 20);   // larger wavefronts amortise the kernels' tails and make the sorted bounces denser: 1M-triangle render 387 (16M) / 412 (32M) / 419 (64M) / 421 (128M) Msamples/s; ~190 B of scratch per path
     auto fail = [&](cudaError_t err, const char* what) {
         cuda_fail(nullptr, err, what, __FILE__, __LINE__);
         b2pt_destroy(ctx);   // releases whatever was created so far
