@@ -92,7 +92,7 @@ typedef struct b2pt_config {
 #define B2PT_FLAG_COUNT_FETCHES 1  /* instrumented traversal: count node / triangle fetches (slower) */
 #define B2PT_FLAG_EXACT_ONLY 2     /* closest-hit queries use only the exact reference-order DFS kernel */
 #define B2PT_FLAG_LANE_KERNELS 4    /* occlusion queries of incoherent batches use the one-ray-per-lane kernels instead of the phase-split pool kernels */
-#define B2PT_FLAG_POOL_EXTEND 16    /* closest-hit queries of incoherent batches use the pool kernels too (measured: no faster) */
+#define B2PT_FLAG_POOL_EXTEND 16    /* closest-hit queries of unordered batches (b2pt_trace_closest; renderer with B2PT_FLAG_NO_SORT) use the pool kernels too (measured: no faster) */
 #define B2PT_FLAG_NO_LEARN_ORDER 8  /* do not re-order wide-node children by measured occlusion rate after the first batch */
 #define B2PT_FLAG_NO_SORT 32        /* renderer: do not put the paths of a bounce in the Morton order of their hit points (no effect on the image) */
 

@@ -11,9 +11,9 @@ Everything that computes runs in ``libb2pt.so`` (hand-written sm_100a CUDA behin
 There is no CPU fallback: importing works without a GPU (so CPU-only tests can check the ABI), but creating
 an :class:`Engine` without an sm_100 device raises.
 """
-from ._capi import (B2ptError, Engine, FLAG_COUNT_FETCHES, FLAG_EXACT_ONLY, FLAG_LANE_KERNELS, FLAG_NO_LEARN_ORDER, FLAG_POOL_EXTEND, LIB_PATH, REFERENCE_LIGHTS,  # noqa: F401
+from ._capi import (B2ptError, Engine, FLAG_COUNT_FETCHES, FLAG_EXACT_ONLY, FLAG_LANE_KERNELS, FLAG_NO_LEARN_ORDER, FLAG_NO_SORT, FLAG_POOL_EXTEND, LIB_PATH, REFERENCE_LIGHTS,  # noqa: F401
                     camera_from_cam13, load_library, make_camera, reference_order)
 from .renderer import B200Renderer, Camera, Scene, Settings  # noqa: F401
 
 __all__ = ["Engine", "B2ptError", "B200Renderer", "Scene", "Camera", "Settings", "reference_order", "load_library",
-           "make_camera", "camera_from_cam13", "FLAG_COUNT_FETCHES", "FLAG_EXACT_ONLY", "FLAG_LANE_KERNELS", "FLAG_NO_LEARN_ORDER", "FLAG_POOL_EXTEND", "REFERENCE_LIGHTS", "LIB_PATH"]
+           "make_camera", "camera_from_cam13", "FLAG_COUNT_FETCHES", "FLAG_EXACT_ONLY", "FLAG_LANE_KERNELS", "FLAG_NO_LEARN_ORDER", "FLAG_NO_SORT", "FLAG_POOL_EXTEND", "REFERENCE_LIGHTS", "LIB_PATH"]

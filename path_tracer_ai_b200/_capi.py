@@ -19,6 +19,7 @@ FLAG_EXACT_ONLY = 2
 FLAG_LANE_KERNELS = 4
 FLAG_NO_LEARN_ORDER = 8
 FLAG_POOL_EXTEND = 16
+FLAG_NO_SORT = 32
 
 
 class Material(C.Structure):
