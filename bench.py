@@ -492,16 +492,26 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel (measured live with CUDA events on the engine's stream) --------
+    # Fetch counts per ray KIND from the instrumented counting build of the same kernels on a 1/16-size frame: one frame
+    # with the lights (closest-hit + shadow rays) and the same frame without lights (the paths do not depend on the lights,
+    # so its closest-hit rays are the same rays and there are no shadow rays); shadow = difference.
     ce = pt.Engine(device=local_rank, flags=pt.FLAG_COUNT_FETCHES, max_paths=args.max_paths)
     ce.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
-    ce.render(cam.c, W // 4, H // 4, 4, B, seed=1234)      # instrumented counting build of the same kernels
+    ce.render(cam.c, W // 4, H // 4, 4, B, seed=1234)
     cst = ce.stats()
     info = ce.accel_info()
+    ce.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, [])
+    ce.render(cam.c, W // 4, H // 4, 4, B, seed=1234)
+    cst0 = ce.stats()
     ce.close()
-    nrays_c = cst["extend_rays"] + cst["shadow_rays"]
-    nodes_per_ray = cst["node_fetches"] / max(nrays_c, 1)
-    tris_per_ray = cst["tri_fetches"] / max(nrays_c, 1)
+    assert cst0["extend_rays"] == cst["extend_rays"] and cst0["shadow_rays"] == 0
     shadow_dominant = agg["shadow_seconds"] >= agg["extend_seconds"]
+    if shadow_dominant:
+        nodes_per_ray = (cst["node_fetches"] - cst0["node_fetches"]) / max(cst["shadow_rays"], 1)
+        tris_per_ray = (cst["tri_fetches"] - cst0["tri_fetches"]) / max(cst["shadow_rays"], 1)
+    else:
+        nodes_per_ray = cst0["node_fetches"] / max(cst0["extend_rays"], 1)
+        tris_per_ray = cst0["tri_fetches"] / max(cst0["extend_rays"], 1)
     # every bounce is in hit-point order, so both ray kinds take the run-to-completion kernels (engine default flags)
     dominant = "k_shadow_rtc" if shadow_dominant else "k_extend_rtc"
     if shadow_dominant:
@@ -541,7 +551,7 @@ def main():
                 "kernel_ms_per_launch": ms_per_launch, "kernel_launches": k_launches,
                 "kernel_share_of_step": k_secs / max(dev_s, 1e-12), "kernel_source_hash": src_hash, "capture": capture_note,
                 "note": "algorithmic bytes (SURVEY 8d) = per-ray queue I/O + mean wide-node fetches x node bytes + mean triangle fetches x 48 B, "
-                        "fetch counts from the counting build of the same kernels on a 1/16-size frame.  The BVH of a 1M-triangle scene "
+                        "fetch counts of this kernel's ray kind from the counting build of the same kernels on a 1/16-size frame.  The BVH of a 1M-triangle scene "
                         "(~100 MB) is L2-resident, so these fetches are mostly served by L1/L2: `frac` is the algorithmic traffic against "
                         "the HBM peak, `frac_hbm_measured` the DRAM bytes ncu counted per launch against the same peak, and `bound` what "
                         "limits the kernel (issue = warp-instruction issue slots, see `issue`)"}
