@@ -404,8 +404,10 @@ __global__ void __launch_bounds__(B2PT_PBLOCK, B2PT_PMINB) k_shadow_pool(DeviceS
 }
 
 // Shadow kernel of the ONE statistics batch per scene (occluder-aware child order, build.cu learn_child_order): same
-// visibility bytes as k_shadow_rtc; every 64th warp also counts box passes and terminal hits per (wide node, slot).
-__global__ void __launch_bounds__(B2PT_SHD_BLOCK) k_shadow_learn(DeviceScene S, Wave W, unsigned* __restrict__ visits, unsigned* __restrict__ hits) {
+// visibility bytes as k_shadow_rtc; every 64th warp runs the instrumented query, which also counts box passes and
+// terminal hits per (wide node, slot) — the other 63 run the production query, so the batch costs what any batch costs
+// (a frame of ONE batch, e.g. BASELINE configs[0] re-uploaded every frame, is all learning batch).
+__global__ void __launch_bounds__(B2PT_SHD_BLOCK, B2PT_SHD_MINB) k_shadow_learn(DeviceScene S, Wave W, unsigned* __restrict__ visits, unsigned* __restrict__ hits) {
     const int nl = S.nlight;
     const int total = W.counters[C_SHADOW];
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -419,7 +421,9 @@ __global__ void __launch_bounds__(B2PT_SHD_BLOCK) k_shadow_learn(DeviceScene S, 
         float dist = vlength(lightDir);
         lightDir = vnormalize(lightDir);
         RayQ r = make_rayq(vadd(P, vmuls(n, 0.001f)), lightDir, B2PT_SUB(dist, 0.001f));   // renderer.hpp:271-275
-        W.vis[e] = any_rtc_learn(S, r, ((j >> 5) & 63) == 0, visits, hits) ? 1 : 0;
+        unsigned n0 = 0, n1 = 0;
+        const bool sampled = ((j >> 5) & 63) == 0;   // warp-uniform
+        W.vis[e] = (sampled ? any_rtc_learn(S, r, true, visits, hits) : any_rtc<false>(S, r, n0, n1)) ? 1 : 0;
     }
 }
 
