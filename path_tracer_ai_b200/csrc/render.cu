@@ -885,7 +885,7 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                     size_t tb = sort_temp_bytes;
                     B2PT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_temp, tb, sort_keys[0], sort_keys[1], sort_vals[0], sort_vals[1], A,
                                                                    0, 32, stream));
-                    launches += 5;   // histogram + four onesweep passes
+                    launches += 6;   // CUB: histogram, exclusive sum, four onesweep passes
                     B2PT_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_join, 0));
                     k_hitinfo<<<(A + B2PT_BIN_BLOCK - 1) / B2PT_BIN_BLOCK, B2PT_BIN_BLOCK, 0, stream>>>(S, Wv, sort_vals[1], &Wv.counters[cur], P);
                     dbg("k_hitinfo", pix_begin, sb, depth);
