@@ -137,6 +137,38 @@ def test_render_edge_cases(engine, cornell):
             engine.render(cam.c, W, H, 4, 3, seed=9)
 
 
+def test_sorted_path_edge_cases(engine):
+    """The same corners on a scene large enough for the sorted, unfused wavefront (hit-point sort, line layout, exact
+    active counts, side-stream fallback): no lights, six lights, one bounce / no bounce, one sample, tiny frames, and a
+    frame whose every batch is smaller than one thread block — all bit-equal to the oracle."""
+    ms = scenes.mesh_scene(6000, seed=11)
+    cam = pt.Camera()
+    lights6 = list(pt.REFERENCE_LIGHTS) + [((0.5, 2.5, -1.0), (1.0, 0.5, 0.25), 3.0), ((-2.0, 1.0, 2.5), (0.2, 0.4, 1.0), 5.0)]
+    l7 = np.float32([list(p) + list(c) + [i] for (p, c, i) in lights6])
+    P = PortOracle(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
+    P6 = PortOracle(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"], lights7=l7)
+    pos, nrm, mat = P.triangles()
+    engine.upload_scene(pos, nrm, mat, ms["materials8"])
+    assert engine.accel_info()["wide_nodes"] > 64
+    for (W, H, SPP, B, seed) in [(48, 27, 2, 1, 4), (48, 27, 1, 6, 5), (16, 9, 3, 0, 6), (2, 2, 5, 4, 7), (3, 2, 1, 8, 8)]:
+        fb = engine.render(cam.c, W, H, SPP, B, seed=seed)
+        ofb, _, _ = P.render(cam13_of(cam), W, H, SPP, B, seed=seed)
+        assert np.array_equal(bits(fb), bits(ofb)), (W, H, SPP, B)
+    engine.upload_scene(pos, nrm, mat, ms["materials8"], lights6)
+    fb = engine.render(cam.c, 48, 27, 3, 4, seed=3)
+    ofb, _, _ = P6.render(cam13_of(cam), 48, 27, 3, 4, seed=3)
+    assert np.array_equal(bits(fb), bits(ofb)) and fb.mean() > 1e-3
+    engine.upload_scene(pos, nrm, mat, ms["materials8"], [])
+    fb = engine.render(cam.c, 48, 27, 2, 4, seed=2)
+    assert not fb.any() and engine.stats()["shadow_rays"] == 0 and engine.stats()["extend_rays"] > 48 * 27 * 2
+    small = pt.Engine(max_paths=1024)     # the engine's minimum batch: 1024 paths
+    small.upload_scene(pos, nrm, mat, ms["materials8"])
+    fb = small.render(cam.c, 40, 30, 3, 5, seed=12)
+    ofb, _, _ = P.render(cam13_of(cam), 40, 30, 3, 5, seed=12)
+    small.close()
+    assert np.array_equal(bits(fb), bits(ofb))
+
+
 def test_degenerate_normals_produce_nan_rays_not_faults(engine):
     """Glass whose vertex normals cancel: the shading normal is NaN, the dielectric branch's refract() returns
     vec3(0) and the Ray ctor normalises it to NaN (renderer.hpp:214-246, ray.hpp:12).  The reference traces that
