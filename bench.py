@@ -61,12 +61,17 @@ KERNEL_SOURCES = ["exact.cuh", "ctx.cuh", "traverse.cuh", "traverse_rtc.cuh", "t
 
 
 def kernel_source_hash() -> str:
-    """Hash of the kernel sources: an ncu capture is only quoted beside numbers measured from the same code."""
+    """Hash of the kernel sources — comments and white space removed, so that only a change of CODE changes it: an ncu
+    capture is only quoted beside numbers measured from the same code."""
+    import re
     h = hashlib.sha256()
     for f in KERNEL_SOURCES:
         p = os.path.join(ROOT, "path_tracer_ai_b200", "csrc", f)
         if os.path.exists(p):
-            h.update(open(p, "rb").read())
+            src = open(p, "r", encoding="utf-8", errors="replace").read()
+            src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)     # block comments
+            src = re.sub(r"//[^\n]*", " ", src)                   # line comments (no string literal in these files holds //)
+            h.update(" ".join(src.split()).encode())
     return h.hexdigest()[:16]
 
 

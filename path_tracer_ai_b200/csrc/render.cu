@@ -4,22 +4,26 @@
 //
 // One frame = pixel chunks x sample chunks of at most `max_paths` camera paths.  Per chunk:
 //   k_raygen                         camera rays (camera.hpp:18-29), T = 1, L = 0
-//   for depth in 0 .. maxBounces-1:
-//     k_extend_rtc (+ k_extend_fallback)  closest hit, one ray per thread; uncertified rays -> exact recursion
+//   for depth in 0 .. maxBounces-1, while paths survive:
+//     k_extend_rtc                    closest hit, one ray per thread; writes the hit record and, in scenes whose
+//                                     bounces are sorted, the (Morton key of the hit point, path slot) pair
+//     k_extend_fallback               uncertified rays -> exact reference recursion (side stream, under the sort)
+//     cub::DeviceRadixSort            the bounce in the Morton order of its hit points (large scenes)
 //     k_hitinfo                       hit point, shading normal, material; bins the path into its material
 //                                     queue (1-pass counting sort on the material type) and into the
-//                                     direct-light queue (fused into k_extend_rtc on small trees)
+//                                     direct-light queue (fused into k_extend_rtc on small trees, nothing sorted)
 //     k_shadow_rtc                    one ray per (vertex, light): any-hit traversal -> visibility byte
 //     k_shade                         direct light from the visible lights (summed in light order),
-//                                     L += T*direct, BSDF sample, T update, next ray -> next queue
+//                                     L += T*direct, BSDF sample, T update, next ray -> next queue (grouped by octant)
+//     (host)                          reads the number of surviving paths: grids and sort sizes of the next depth
 //   k_resolve                        per pixel: samples added in sample order (renderer.hpp:69-72)
 // k_finalize divides by spp (renderer.hpp:75-81).
 //
-// Path state lives in SoA float4 arrays indexed by path slot p = s_local * npix_chunk + pixel_local
-// (sample-major: neighbouring threads are neighbouring pixels); queues hold path slots.  All
-// arithmetic that decides a path (hit, direction, throughput) uses the exact.cuh operations, and the
-// RNG is Philox4x32-10 keyed by (seed; pixel, sample, depth, draw): the image is a pure function of
-// (scene, camera, settings, seed), independent of chunking, queue order and GPU count.
+// Path state: eight float4 fields per path slot p = s_local * npix_chunk + pixel_local (sample-major: neighbouring
+// slots are neighbouring pixels), one 128-byte line per slot in sorted scenes, one array per field in small ones
+// (struct PathField); queues hold path slots.  All arithmetic that decides a path (hit, direction, throughput) uses
+// the exact.cuh operations, and the RNG is Philox4x32-10 keyed by (seed; pixel, sample, depth, draw): the image is a
+// pure function of (scene, camera, settings, seed), independent of chunking, queue order, sorting and GPU count.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
