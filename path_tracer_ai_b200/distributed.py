@@ -45,7 +45,14 @@ def combine_frames(buf, dst: int = 0, group=None):
 
 
 def render_distributed(engine, cam, width, height, spp_total, bounces, d_rgb, part, seed=1234, dst=0, group=None):
-    """Renders this rank's share into the CUDA tensor `d_rgb` (W*H*3 float32) and combines on `dst`."""
+    """Renders this rank's share into the CUDA tensor `d_rgb` (W*H*3 float32) and combines on `dst`.
+
+    Stream contract (include/b2pt.h): the engine works on its own non-blocking stream and returns when the frame is
+    complete, but it does not order itself after work queued on other streams — so whatever torch still has in flight on
+    `d_rgb` (the previous frame's reduce, a fill) is waited for first."""
+    if d_rgb.is_cuda:
+        import torch
+        torch.cuda.current_stream(d_rgb.device).synchronize()
     engine.render_device(cam, width, height, spp_total, bounces, d_rgb.data_ptr(), seed=seed, part=part)
     stats = engine.stats()
     combine_frames(d_rgb, dst, group)
