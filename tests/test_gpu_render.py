@@ -328,10 +328,16 @@ def test_progressive_accumulation_is_bit_identical_to_the_one_shot_frame(built, 
     assert np.array_equal(r.tonemapped(), reference_tonemap(r.frameBuffer, 2.2))
 
 
-def test_multi_device_renderer_is_bit_identical(built, cornell):
+@pytest.mark.parametrize("which", ["cornell", "mesh"])
+def test_multi_device_renderer_is_bit_identical(built, cornell, which):
     """b2pt_multi_*: one object, N contexts (here N contexts on the devices that exist — an ordinal may repeat, which
-    exercises partition + gather on a single GPU too).  Frame and PNG bytes equal the single-device renderer's."""
+    exercises partition + gather on a single GPU too).  Frame and PNG bytes equal the single-device renderer's, on the
+    small-scene (fused) path and on the sorted path of a 6000-triangle mesh scene."""
     import torch
+    if which == "mesh":
+        ms = scenes.mesh_scene(6000, seed=11)
+        cornell = pt.Scene()
+        cornell.setContents(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
     st = pt.Settings(width=200, height=120, samplesPerPixel=6, maxBounces=4)
     one = pt.B200Renderer(st, seed=5)
     one.initialize(); one.uploadScene(cornell)
