@@ -856,11 +856,11 @@ int render_frame(b2pt_ctx* ctx, const b2pt_camera* cam, const b2pt_settings* st,
                 dbg("k_begin_bounce", pix_begin, sb, depth);
                 const int* list = depth == 0 ? nullptr : Wv.q_active[cur];
                 ev();
-                // Shadow rays of the bounces of a scene big enough for a warp's rays to diverge take the phase-split pool
-                // kernel (1M-triangle scene, 32M-path batches: shadow 1276 -> 1167 ms per frame); closest hit stays with the
-                // run-to-completion kernel, which the pool variant does not beat (850 vs 801 ms): B2PT_FLAG_POOL_EXTEND.
-                // With the bounces in hit-point order (sort_hits) the shadow rays of a warp are near-identical again and the
-                // run-to-completion kernel wins (16 spp, 32M paths: sorted + pool 61 ms, sorted + rtc 42 ms, unsorted + pool 73 ms).
+                // Kernel variants.  With the bounces in hit-point order (sort_hits, the default for large scenes) the rays of a
+                // warp are near-identical and both ray kinds take the run-to-completion kernels (shadow rays of a 32M-path batch:
+                // sorted + rtc 42 ms, sorted + pool 61 ms, unsorted + pool 73 ms, unsorted + rtc 80 ms).  Unsorted bounces
+                // (B2PT_FLAG_NO_SORT) keep the phase-split pool kernel for shadow rays, and for closest hit with
+                // B2PT_FLAG_POOL_EXTEND (it does not beat the run-to-completion kernel there: 850 vs 801 ms per C3 frame).
                 const bool pooled = !fused && depth > 0 && !sort_hits && !(ctx->flags & B2PT_FLAG_LANE_KERNELS);
                 const unsigned pgrid = (unsigned)std::min<long long>(((long long)A + B2PT_PBLOCK * B2PT_PR - 1) / (B2PT_PBLOCK * B2PT_PR), (long long)ctx->sm_count * 8);
                 if (pooled && (ctx->flags & B2PT_FLAG_POOL_EXTEND)) {
