@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the configs[3] closest-hit microbench")
     ap.add_argument("--c4-rays", type=int, default=100_000_000)
-    ap.add_argument("--c4-check", type=int, default=4_000_000, help="rays of the microbench compared with the reference CPU BVH")
+    ap.add_argument("--c4-check", type=int, default=10_000_000, help="rays of the microbench compared with the reference CPU BVH")
     ap.add_argument("--max-paths", type=int, default=DEFAULT_MAX_PATHS)
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (reported in config.spp)")
     ap.add_argument("--flags", type=int, default=0, help="B2PT_FLAG_* bits for the timed engine (experiments; 0 = product defaults)")

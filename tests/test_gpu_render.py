@@ -57,6 +57,24 @@ def test_render_mesh_scene_bit_exact(engine):
     assert fb.mean() > 1e-3
 
 
+def test_render_1m_triangle_scene_bit_exact(engine):
+    """BASELINE configs[2]'s scene at full triangle count (1M tessellated triangles + the loader's room, mixed
+    materials), a 192x108 frame of 2 spp and 8 bounces: the sorted wavefront on the device-built tree returns the
+    oracle renderer's bits (the CPU side is 41k camera paths — seconds)."""
+    ms = scenes.mesh_scene(1_000_000, seed=1234)
+    sc = pt.Scene()
+    sc.setContents(ms["pos"], ms["nrm"], ms["mat"], ms["materials8"])
+    P = PortOracle(*prebuild_from_scene(sc), sc.materials8)
+    assert np.array_equal(P.order(), sc.order)
+    engine.upload_scene(sc.pos, sc.nrm, sc.mat, sc.materials8, sc.lights)
+    assert engine.accel_info()["hoisted_leaves"] >= 1
+    cam = pt.Camera()
+    fb = engine.render(cam.c, 192, 108, 2, 8, seed=31)
+    ofb, _, _ = P.render(cam13_of(cam), 192, 108, 2, 8, seed=31)
+    assert np.array_equal(bits(fb), bits(ofb)), f"max abs diff {np.abs(fb - ofb).max()}"
+    assert fb.mean() > 1e-3
+
+
 def test_render_independent_of_bounce_order_and_kernel_variant(built):
     """The hit-point sort of every bounce, the direction-octant grouping of the next rays and the kernel variant chosen for
     the shadow rays only change the ORDER in which paths are processed: the frame is the same bits with the sort switched
