@@ -308,14 +308,15 @@ __global__ void __launch_bounds__(FUSED ? B2PT_EXT_BLOCK_FUSED : B2PT_EXT_BLOCK,
     int p = 0;
     if (k < total) {
         p = list ? list[k] : k;
-        float4 o4 = W.ro[p], d4 = W.rd[p];
+        // path state is read once and written once here: streaming accesses keep L1 for the nodes, the triangles and the stack
+        float4 o4 = __ldcs(&W.ro[p]), d4 = __ldcs(&W.rd[p]);
         RayQ r = make_rayq_normalised(f4v(o4), f4v(d4), B2PT_INF);
         HitRec h;
         bool ok = closest_rtc<COUNT>(S, r, h, n_nodes, n_tris);
         if (!FUSED) {
-            W.hit[p] = make_float4(h.t, __int_as_float(h.tri), h.u, h.v);
+            __stcs(&W.hit[p], make_float4(h.t, __int_as_float(h.tri), h.u, h.v));
             // (key, slot) pair of the hit-point order; an uncertified ray's key comes from its provisional hit — only an order
-            if (order_keys) { order_keys[k] = hit_point_key(r.o, r.d, h, S.coord_bound); order_vals[k] = p; }
+            if (order_keys) { __stcs(&order_keys[k], hit_point_key(r.o, r.d, h, S.coord_bound)); __stcs(&order_vals[k], p); }
         } else if (ok) e = hit_epilogue(S, W, p, r.o, r.d, h);
         if (!ok) W.q_fallback[atomicAdd(&W.counters[C_FALLBACK], 1)] = p;
     }

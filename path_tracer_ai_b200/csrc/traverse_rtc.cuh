@@ -52,9 +52,8 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
             }
         }
     }
-    // stack of (child code, entry)
-    uint32_t scode[B2PT_RTC_STACK];
-    float sent[B2PT_RTC_STACK];
+    // stack of (child code, entry distance bits): one 8-byte local-memory access per entry
+    uint2 stk[B2PT_RTC_STACK];
     int sp = 0;
     uint32_t cur = 0;             // root wide node
     while (S.nwide > 0) {
@@ -74,8 +73,12 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
                     if (n4.pass[s] && tmin <= cull) {
                         // insert so that entries in [base, sp) are sorted by decreasing entry distance
                         int j = sp++;
-                        while (j > base && sent[j - 1] < tmin) { sent[j] = sent[j - 1]; scode[j] = scode[j - 1]; --j; }
-                        sent[j] = tmin; scode[j] = n4.code[s];
+                        while (j > base) {
+                            const uint2 prev = stk[j - 1];
+                            if (!(__uint_as_float(prev.y) < tmin)) break;
+                            stk[j] = prev; --j;
+                        }
+                        stk[j] = make_uint2(n4.code[s], __float_as_uint(tmin));
                     }
                 }
             }
@@ -101,8 +104,8 @@ __device__ __forceinline__ bool closest_rtc(const DeviceScene& S, const RayQ& r,
         // pop
         bool got = false;
         while (sp > 0) {
-            --sp;
-            if (sent[sp] <= cull) { cur = scode[sp]; got = true; break; }
+            const uint2 e = stk[--sp];
+            if (__uint_as_float(e.y) <= cull) { cur = e.x; got = true; break; }
         }
         if (!got) break;
     }
