@@ -140,14 +140,16 @@ __device__ __forceinline__ bool any_rtc(const DeviceScene& S, const RayQ& r, uns
             if (sp > B2PT_RTC_STACK - 8) { HitRec h; closest_exact_dfs(S, r, h); return h.tri >= 0; }
             const WideNode* nd = &S.wide[cur];
             if (COUNT) ++n_nodes;
+            uint32_t pend = B2PT_CHILD_EMPTY;   // the last passing child so far: entered next, without a stack round trip
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 Node4 n4;
                 node_test4(nd, k, r, n4);
 #pragma unroll
                 for (int s = 0; s < 4; ++s)
-                    if (n4.pass[s]) scode[sp++] = n4.code[s];
+                    if (n4.pass[s]) { if (pend != B2PT_CHILD_EMPTY) scode[sp++] = pend; pend = n4.code[s]; }
             }
+            if (pend != B2PT_CHILD_EMPTY) { cur = pend; continue; }
         } else {
             int first = cur & 0x0FFFFFFF, cnt = ((cur >> 28) & 7) + 1;
             for (int i = first; i < first + cnt; ++i) {
