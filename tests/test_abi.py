@@ -83,3 +83,19 @@ def test_product_never_imports_oracle():
                         or "libpt_oracle" in text or "libref_oracle" in text:
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_sass_keeps_the_parity_arithmetic_scalar(built):
+    """ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one rounding where the reference has two), so the
+    kernels must not use Blackwell's packed fp32 instructions at all: no FMUL2 / FADD2 / FFMA2 in libb2pt.so, and the
+    traversal kernels do their arithmetic with scalar FMUL / FADD (tools/sass_mix.py, profiles/r02_sass_mix.txt)."""
+    import shutil
+    import path_tracer_ai_b200 as pt
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", pt.LIB_PATH], capture_output=True, text=True).stdout
+    assert "Function :" in sass and "k_extend_rtc" in sass and "k_shadow_rtc" in sass
+    for packed in ("FMUL2", "FADD2", "FFMA2"):
+        assert f" {packed} " not in sass, packed
+    assert sass.count(" FMUL ") > 1000 and sass.count(" FADD ") > 1000
